@@ -1,0 +1,118 @@
+/*
+ * ramdsir.h -- C ABI of the B200-native Random Amplitude Mixup (RAM) library (libramdsir.so).
+ *
+ * This is the drop-in boundary for the one hot path of zzzqzhou/RAM-DSIR that this repo
+ * re-implements.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference checkout, code/dataset/fundus.py == code/dataset/prostate.py):
+ *
+ *   ramdsir_bank_build_f32   <- extract_amp_spectrum(img_np)            fundus.py:13-19
+ *                               (only the low band the blend reads: fftshift(amp)[:, h1:h2, w1:w2],
+ *                                fundus.py:22-33)
+ *   ramdsir_mix_f32          <- source_to_target_freq(src, amp_trg, L)  fundus.py:41-61
+ *                               + low_freq_mutate_np                    fundus.py:21-39
+ *                               + caller epilogue clip/normalise        fundus.py:215,222-223 / prostate.py:188
+ *   ramdsir_mix_host_f32     <- the same, as called from the data loader with HOST arrays
+ *                               (Fundus_Multi.__getitem__ fundus.py:197-225, Prostate_Multi prostate.py:177-202)
+ *   ramdsir_band_halfwidth   <- b = floor(min(h, w) * L)                fundus.py:26
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all *_dev pointers are BORROWED device pointers on the current
+ *     CUDA device, 16-byte aligned, densely packed NCHW float32; `stream` is a cudaStream_t cast to
+ *     void* (NULL = legacy default stream).  Calls are asynchronous and stream-ordered.
+ *   - the library owns nothing persistent except per-(device, H, W, b) twiddle tables built lazily
+ *     on first use (a few KB each) and, for the *_host entry, an explicit pipeline handle.
+ *   - every function returns RAMDSIR_OK (0) or an error code; ramdsir_last_error() gives the
+ *     thread-local message.  There is no CPU fallback and no cuFFT: an unsupported shape is an error.
+ *   - amplitude bank layout: bank[n][c][kh + b][kw + b] = |FFT2(img n, channel c)[kh mod H, kw mod W]|,
+ *     kh, kw in [-b, b]  (numpy's unnormalised forward transform), i.e. exactly
+ *     np.fft.fftshift(extract_amp_spectrum(img))[:, cH-b:cH+b+1, cW-b:cW+b+1].
+ *   - partner selection and ratio are drawn on the host with the reference's own RNG calls and passed
+ *     in: partner_idx[i] indexes the bank, ratio = ratio_k[i] / ratio_den weights the SOURCE amplitude
+ *     (fundus.py:35,37; the reference uses ratio_k in 1..10, ratio_den = 10).  An out-of-range
+ *     partner index poisons that image's output with NaN instead of reading out of bounds.
+ *   - epilogue: out = clamp(v, clip_lo, clip_hi) * scale + shift.  fundus: (0, 255, 1/127.5, -1);
+ *     prostate: (-1, 1, 1, 0); "no epilogue": (-INF, INF, 1, 0).
+ */
+#ifndef RAMDSIR_H_
+#define RAMDSIR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAMDSIR_OK 0
+#define RAMDSIR_ERR_INVALID 1      /* bad argument (null pointer, non-positive size, misalignment) */
+#define RAMDSIR_ERR_UNSUPPORTED 2  /* shape / band not supported by any CUDA path */
+#define RAMDSIR_ERR_CUDA 3         /* a CUDA runtime call failed; see ramdsir_last_error() */
+#define RAMDSIR_ERR_WORKSPACE 4    /* workspace too small; see ramdsir_workspace_bytes() */
+
+/* kernel families, as reported by ramdsir_path() */
+#define RAMDSIR_PATH_NONE 0
+#define RAMDSIR_PATH_FUSED 1      /* one CTA per plane, band buffers resident in shared memory */
+#define RAMDSIR_PATH_MULTIPASS 2  /* large images: band buffers in an L2-resident workspace */
+#define RAMDSIR_PATH_GENERIC 3    /* any H, W: direct band-pruned DFT kernels */
+
+int ramdsir_version(void);
+const char* ramdsir_last_error(void);
+
+/* b = floor(min(H, W) * L) evaluated in float64, as fundus.py:26 does. */
+int ramdsir_band_halfwidth(int H, int W, double L);
+
+/* Which kernel family serves this shape (RAMDSIR_PATH_*). */
+int ramdsir_path(int C, int H, int W, int b);
+
+/* Testing knob: route every later call through the generic kernels (RAMDSIR_PATH_GENERIC) so two
+ * independent CUDA implementations can be compared; 0 restores automatic selection. */
+int ramdsir_force_path(int path);
+
+/* Scratch bytes needed to process `n_images` images of this shape in one call (0 for the fused path). */
+size_t ramdsir_workspace_bytes(int n_images, int C, int H, int W, int b);
+
+/* K3: amplitude bank.  imgs_dev [N, C, H, W] -> bank_dev [N, C, 2b+1, 2b+1]. */
+int ramdsir_bank_build_f32(const float* imgs_dev, float* bank_dev, int N, int C, int H, int W, int b,
+                           void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* K1/K2: RAM.  src_dev [B, C, H, W] -> out_dev [B, C, H, W]; out_dev must not alias src_dev (the source is read twice). */
+int ramdsir_mix_f32(const float* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
+                    const int32_t* ratio_k_dev, float* out_dev, int B, int C, int H, int W, int b,
+                    int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * Strict per-sample drop-ins (correctness shims for code that calls the reference functions directly).
+ *   ramdsir_amp_spectrum_f32 <- extract_amp_spectrum: FULL amplitude spectrum [N, C, H, W], un-shifted
+ *                               (fundus.py:13-19).  Direct DFT, any H and W; workspace from
+ *                               ramdsir_amp_spectrum_workspace_bytes().
+ *   ramdsir_band_blend_f32   <- low_freq_mutate_np with the ratio numerator supplied by the caller
+ *                               (fundus.py:21-39): out = amp_src, band blended with amp_trg.
+ */
+size_t ramdsir_amp_spectrum_workspace_bytes(int N, int C, int H, int W);
+int ramdsir_amp_spectrum_f32(const float* imgs_dev, float* amp_dev, int N, int C, int H, int W,
+                             void* workspace_dev, size_t workspace_bytes, void* stream);
+int ramdsir_band_blend_f32(const float* amp_src_dev, const float* amp_trg_dev, float* out_dev, int C, int H, int W,
+                           int b, int ratio_k, int ratio_den, void* stream);
+
+/*
+ * Host-buffer entry point (what a data-loader process calls).  A pipeline handle owns device
+ * staging buffers and three streams; ramdsir_mix_host_f32 splits the batch into chunks and
+ * overlaps host->device copy, the RAM kernel and device->host copy.  src_host / out_host should be
+ * pinned (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous; pageable memory
+ * works but serialises.  The call returns after out_host is complete.
+ */
+typedef struct ramdsir_pipe ramdsir_pipe_t;
+int ramdsir_pipe_create(ramdsir_pipe_t** pipe, int max_chunk_images, int C, int H, int W, int b);
+void ramdsir_pipe_destroy(ramdsir_pipe_t* pipe);
+int ramdsir_mix_host_f32(ramdsir_pipe_t* pipe, const float* src_host, const float* bank_dev,
+                         const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host,
+                         int B, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale,
+                         float shift);
+/* number of kernel launches the library has issued on this process so far (bench bookkeeping) */
+uint64_t ramdsir_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAMDSIR_H_ */

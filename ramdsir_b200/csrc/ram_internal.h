@@ -1,0 +1,49 @@
+// Internal declarations shared by the translation units of libramdsir.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/ramdsir.h"
+#include "ram_fused_core.cuh"
+
+namespace ramdsir {
+
+// thread-local error text (ramdsir_last_error)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define RD_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct MixArgs {
+  const float* src;
+  const float* bank;
+  const int64_t* pidx;
+  const int32_t* rk;
+  float* out;
+  int B, C, H, W, b, n_bank, ratio_den;
+  Epilogue ep;
+};
+
+// fused single-CTA-per-plane path (ram_fused.cu)
+bool fused_supported(int H, int W, int b);
+int fused_mix(const MixArgs& a, cudaStream_t st);
+int fused_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st);
+
+// any-shape direct band-pruned DFT path (ram_generic.cu)
+bool generic_supported(int H, int W, int b);
+size_t generic_workspace_bytes(int n_images, int C, int H, int W, int b);
+int generic_mix(const MixArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
+int generic_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, void* ws, size_t ws_bytes, cudaStream_t st);
+
+
+// drop-in helpers for the per-sample reference API (ram_generic.cu)
+size_t full_amp_workspace_bytes(int N, int C, int H, int W);
+int full_amp(const float* imgs, float* amp, int N, int C, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st);
+int band_blend(const float* a_src, const float* a_trg, float* out, int C, int H, int W, int b, int ratio_k, int ratio_den, cudaStream_t st);
+
+}  // namespace ramdsir

@@ -1,0 +1,246 @@
+// extern "C" surface of libramdsir.so (see include/ramdsir.h for the contract and the reference
+// interfaces each entry point replaces).
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "ram_internal.h"
+
+namespace ramdsir {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return RAMDSIR_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int check_shape(int n, int C, int H, int W, int b) {
+  if (n < 0 || C < 1 || H < 1 || W < 1 || b < 0) {
+    set_error("invalid shape n=%d C=%d H=%d W=%d b=%d", n, C, H, W, b);
+    return RAMDSIR_ERR_INVALID;
+  }
+  if (2 * b + 1 > (H < W ? H : W)) {
+    set_error("band (2*%d+1) exceeds the spectrum of a %dx%d image", b, H, W);
+    return RAMDSIR_ERR_UNSUPPORTED;
+  }
+  return RAMDSIR_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static std::atomic<int> g_force_path{0};
+
+static int path_of(int H, int W, int b) {
+  const int force = g_force_path.load(std::memory_order_relaxed);
+  if (force == RAMDSIR_PATH_GENERIC) return generic_supported(H, W, b) ? RAMDSIR_PATH_GENERIC : RAMDSIR_PATH_NONE;
+  if (fused_supported(H, W, b)) return RAMDSIR_PATH_FUSED;
+  if (generic_supported(H, W, b)) return RAMDSIR_PATH_GENERIC;
+  return RAMDSIR_PATH_NONE;
+}
+
+}  // namespace ramdsir
+
+using namespace ramdsir;
+
+extern "C" {
+
+int ramdsir_version(void) { return 100; }  // 0.1.0
+
+const char* ramdsir_last_error(void) { return g_err; }
+
+int ramdsir_band_halfwidth(int H, int W, double L) {
+  const double m = (double)(H < W ? H : W);
+  return (int)std::floor(m * L);  // fundus.py:26, float64
+}
+
+int ramdsir_force_path(int path) {
+  if (path != 0 && path != RAMDSIR_PATH_GENERIC) {
+    set_error("force_path: only 0 (auto) or RAMDSIR_PATH_GENERIC can be forced");
+    return RAMDSIR_ERR_INVALID;
+  }
+  g_force_path.store(path, std::memory_order_relaxed);
+  return RAMDSIR_OK;
+}
+
+int ramdsir_path(int C, int H, int W, int b) {
+  if (check_shape(0, C, H, W, b)) return RAMDSIR_PATH_NONE;
+  return path_of(H, W, b);
+}
+
+size_t ramdsir_workspace_bytes(int n_images, int C, int H, int W, int b) {
+  if (check_shape(n_images, C, H, W, b)) return 0;
+  return path_of(H, W, b) == RAMDSIR_PATH_GENERIC ? generic_workspace_bytes(n_images, C, H, W, b) : 0;
+}
+
+int ramdsir_bank_build_f32(const float* imgs_dev, float* bank_dev, int N, int C, int H, int W, int b,
+                           void* workspace_dev, size_t workspace_bytes, void* stream) {
+  int rc = check_shape(N, C, H, W, b);
+  if (rc) return rc;
+  if (N == 0) return RAMDSIR_OK;
+  if (!imgs_dev || !bank_dev || !aligned16(imgs_dev)) {
+    set_error("bank_build: null or misaligned pointer");
+    return RAMDSIR_ERR_INVALID;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (path_of(H, W, b)) {
+    case RAMDSIR_PATH_FUSED: return fused_bank(imgs_dev, bank_dev, N, C, H, W, b, st);
+    case RAMDSIR_PATH_GENERIC: return generic_bank(imgs_dev, bank_dev, N, C, H, W, b, workspace_dev, workspace_bytes, st);
+  }
+  set_error("no CUDA path for H=%d W=%d b=%d (and there is no CPU fallback)", H, W, b);
+  return RAMDSIR_ERR_UNSUPPORTED;
+}
+
+int ramdsir_mix_f32(const float* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
+                    const int32_t* ratio_k_dev, float* out_dev, int B, int C, int H, int W, int b,
+                    int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
+                    void* workspace_dev, size_t workspace_bytes, void* stream) {
+  int rc = check_shape(B, C, H, W, b);
+  if (rc) return rc;
+  if (B == 0) return RAMDSIR_OK;
+  if (!src_dev || !bank_dev || !partner_idx_dev || !ratio_k_dev || !out_dev || !aligned16(src_dev) || !aligned16(out_dev)) {
+    set_error("mix: null or misaligned pointer");
+    return RAMDSIR_ERR_INVALID;
+  }
+  if (n_bank < 1 || ratio_den < 1) {
+    set_error("mix: n_bank=%d ratio_den=%d must be positive", n_bank, ratio_den);
+    return RAMDSIR_ERR_INVALID;
+  }
+  if (src_dev == out_dev) {
+    set_error("mix: in-place operation is not supported (the source is read twice)");
+    return RAMDSIR_ERR_INVALID;
+  }
+  MixArgs a{src_dev, bank_dev, partner_idx_dev, ratio_k_dev, out_dev, B, C, H, W, b, n_bank, ratio_den,
+            Epilogue{clip_lo, clip_hi, scale, shift}};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (path_of(H, W, b)) {
+    case RAMDSIR_PATH_FUSED: return fused_mix(a, st);
+    case RAMDSIR_PATH_GENERIC: return generic_mix(a, workspace_dev, workspace_bytes, st);
+  }
+  set_error("no CUDA path for H=%d W=%d b=%d (and there is no CPU fallback)", H, W, b);
+  return RAMDSIR_ERR_UNSUPPORTED;
+}
+
+size_t ramdsir_amp_spectrum_workspace_bytes(int N, int C, int H, int W) {
+  if (N < 0 || C < 1 || H < 1 || W < 1) return 0;
+  return full_amp_workspace_bytes(N, C, H, W);
+}
+
+int ramdsir_amp_spectrum_f32(const float* imgs_dev, float* amp_dev, int N, int C, int H, int W,
+                             void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (N < 0 || C < 1 || H < 1 || W < 1 || !imgs_dev || !amp_dev) {
+    set_error("amp_spectrum: invalid arguments");
+    return RAMDSIR_ERR_INVALID;
+  }
+  return full_amp(imgs_dev, amp_dev, N, C, H, W, workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ramdsir_band_blend_f32(const float* amp_src_dev, const float* amp_trg_dev, float* out_dev, int C, int H, int W,
+                           int b, int ratio_k, int ratio_den, void* stream) {
+  if (C < 1 || H < 1 || W < 1 || b < 0 || ratio_den < 1 || !amp_src_dev || !amp_trg_dev || !out_dev) {
+    set_error("band_blend: invalid arguments");
+    return RAMDSIR_ERR_INVALID;
+  }
+  return band_blend(amp_src_dev, amp_trg_dev, out_dev, C, H, W, b, ratio_k, ratio_den, reinterpret_cast<cudaStream_t>(stream));
+}
+
+uint64_t ramdsir_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer pipeline: NSLOT device slots, one stream each (H2D -> kernel -> D2H in stream order);
+// consecutive chunks go to different slots so the copy engines and the SMs overlap.
+struct ramdsir_pipe {
+  static constexpr int NSLOT = 3;
+  int chunk, C, H, W, b;
+  size_t img_elems, ws_bytes;
+  cudaStream_t st[NSLOT];
+  float* d_src[NSLOT];
+  float* d_out[NSLOT];
+  int64_t* d_pidx[NSLOT];
+  int32_t* d_rk[NSLOT];
+  void* d_ws[NSLOT];
+};
+
+int ramdsir_pipe_create(ramdsir_pipe_t** pipe, int max_chunk_images, int C, int H, int W, int b) {
+  if (!pipe || max_chunk_images < 1) {
+    set_error("pipe_create: invalid arguments");
+    return RAMDSIR_ERR_INVALID;
+  }
+  int rc = check_shape(max_chunk_images, C, H, W, b);
+  if (rc) return rc;
+  if (path_of(H, W, b) == RAMDSIR_PATH_NONE) {
+    set_error("no CUDA path for H=%d W=%d b=%d", H, W, b);
+    return RAMDSIR_ERR_UNSUPPORTED;
+  }
+  ramdsir_pipe* p = new ramdsir_pipe();
+  memset(p, 0, sizeof(*p));
+  p->chunk = max_chunk_images; p->C = C; p->H = H; p->W = W; p->b = b;
+  p->img_elems = (size_t)C * H * W;
+  p->ws_bytes = ramdsir_workspace_bytes(max_chunk_images, C, H, W, b);
+  for (int i = 0; i < ramdsir_pipe::NSLOT; ++i) {
+    cudaError_t e = cudaStreamCreateWithFlags(&p->st[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_src[i], p->img_elems * sizeof(float) * p->chunk);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_out[i], p->img_elems * sizeof(float) * p->chunk);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_pidx[i], sizeof(int64_t) * p->chunk);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_rk[i], sizeof(int32_t) * p->chunk);
+    if (e == cudaSuccess && p->ws_bytes) e = cudaMalloc(&p->d_ws[i], p->ws_bytes);
+    if (e != cudaSuccess) {
+      ramdsir_pipe_destroy(p);
+      return cuda_fail(e, "pipe_create allocation");
+    }
+  }
+  *pipe = p;
+  return RAMDSIR_OK;
+}
+
+void ramdsir_pipe_destroy(ramdsir_pipe_t* p) {
+  if (!p) return;
+  for (int i = 0; i < ramdsir_pipe::NSLOT; ++i) {
+    if (p->st[i]) { cudaStreamSynchronize(p->st[i]); cudaStreamDestroy(p->st[i]); }
+    cudaFree(p->d_src[i]); cudaFree(p->d_out[i]); cudaFree(p->d_pidx[i]); cudaFree(p->d_rk[i]); cudaFree(p->d_ws[i]);
+  }
+  delete p;
+}
+
+int ramdsir_mix_host_f32(ramdsir_pipe_t* p, const float* src_host, const float* bank_dev,
+                         const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host,
+                         int B, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale,
+                         float shift) {
+  if (!p || !src_host || !bank_dev || !partner_idx_host || !ratio_k_host || !out_host || B < 0) {
+    set_error("mix_host: invalid arguments");
+    return RAMDSIR_ERR_INVALID;
+  }
+  for (int i = 0; i < B; ++i)
+    if (partner_idx_host[i] < 0 || partner_idx_host[i] >= n_bank) {
+      set_error("mix_host: partner_idx[%d]=%lld outside the bank of %d images", i, (long long)partner_idx_host[i], n_bank);
+      return RAMDSIR_ERR_INVALID;
+    }
+  int slot = 0;
+  for (int i0 = 0; i0 < B; i0 += p->chunk, slot = (slot + 1) % ramdsir_pipe::NSLOT) {
+    const int n = (B - i0 < p->chunk) ? B - i0 : p->chunk;
+    cudaStream_t st = p->st[slot];
+    const size_t off = (size_t)i0 * p->img_elems, bytes = (size_t)n * p->img_elems * sizeof(float);
+    RD_CUDA(cudaMemcpyAsync(p->d_src[slot], src_host + off, bytes, cudaMemcpyHostToDevice, st));
+    RD_CUDA(cudaMemcpyAsync(p->d_pidx[slot], partner_idx_host + i0, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+    RD_CUDA(cudaMemcpyAsync(p->d_rk[slot], ratio_k_host + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    int rc = ramdsir_mix_f32(p->d_src[slot], bank_dev, p->d_pidx[slot], p->d_rk[slot], p->d_out[slot], n, p->C, p->H,
+                             p->W, p->b, n_bank, ratio_den, clip_lo, clip_hi, scale, shift, p->d_ws[slot], p->ws_bytes, st);
+    if (rc) return rc;
+    RD_CUDA(cudaMemcpyAsync(out_host + off, p->d_out[slot], bytes, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < ramdsir_pipe::NSLOT; ++i) RD_CUDA(cudaStreamSynchronize(p->st[i]));
+  return RAMDSIR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ramdsir_b200) against
+  (1) golden vectors minted from the unmodified reference (tests/golden, oracle/gen_golden.py),
+  (2) the numpy float64 oracle on seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full batch sizes.
+Tolerance (BASELINE.json north_star): relative L2 <= 1e-5 and max-abs <= 1e-4 on NORMALISED
+intensities (fundus: after clip[0,255]/127.5-1; prostate: after clip[-1,1]) vs the float64 path.
+Selection (partner index, band geometry) is integer work and must be bit-exact.
+"""
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ram_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_TOL = 1e-5
+MAX_ABS_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def R():
+    import ramdsir_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return ramdsir_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def check(got, want, what=""):
+    r, m = O.rel_l2(got, want), O.max_abs(got, want)
+    assert r <= REL_L2_TOL and m <= MAX_ABS_TOL, "%s rel_l2=%.3e max_abs=%.3e" % (what, r, m)
+    return r, m
+
+
+def norm_epi_for(src):
+    """Pick the reference's epilogue by value range: uint8-valued -> fundus, else prostate."""
+    return O.FUNDUS_EPILOGUE if float(np.max(src)) > 2.0 else O.PROSTATE_EPILOGUE
+
+
+def gpu_mix(R, src_nchw, partners_nchw, pidx, rk, L, epi, force_generic=False):
+    from ramdsir_b200 import _lib
+    lib = _lib.load()
+    if force_generic:
+        _lib.check(lib.ramdsir_force_path(_lib.PATH_GENERIC))
+    try:
+        bank = R.build_amp_bank(dev(partners_nchw), L=L)
+        out = R.ram_mix_batch(dev(src_nchw), bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3])
+        torch.cuda.synchronize()
+        return out.cpu().numpy(), bank.cpu().numpy()
+    finally:
+        if force_generic:
+            lib.ramdsir_force_path(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) golden vectors from the reference
+def test_golden_small_shapes(R, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ram_small.npz"))
+    for key in g["names"]:
+        L, k = g[key + "_meta"]
+        src, trg, ref_hwc = g[key + "_src"], g[key + "_trg"], g[key + "_out"]
+        epi = norm_epi_for(src)
+        got, _ = gpu_mix(R, src[None], trg[None], [0], [int(k)], float(L), epi)
+        want = O.epilogue(ref_hwc.transpose(2, 0, 1), *epi)
+        check(got[0], want, key)
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_golden_fundus256(R, golden_dir, force_generic):
+    g = np.load(os.path.join(golden_dir, "ram_fundus256.npz"))
+    L, k = g["meta"]
+    src, trg = g["src"].astype(np.float32), g["trg"].astype(np.float32)
+    got, _ = gpu_mix(R, src[None], trg[None], [0], [int(k)], float(L), O.FUNDUS_EPILOGUE, force_generic)
+    want = O.epilogue(g["out_f64"].transpose(2, 0, 1), *O.FUNDUS_EPILOGUE)
+    check(got[0], want, "fundus256")
+    # and unclipped / unnormalised, relative to the 0..255 range
+    got_raw, _ = gpu_mix(R, src[None], trg[None], [0], [int(k)], float(L), (-math.inf, math.inf, 1.0, 0.0), force_generic)
+    assert O.rel_l2(got_raw[0], g["out_f64"].transpose(2, 0, 1)) <= REL_L2_TOL
+
+
+@pytest.mark.parametrize("tag", ["c1", "c3"])
+def test_golden_prostate384(R, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "ram_prostate384.npz"))
+    L, k = g[tag + "_meta"]
+    src, trg = g[tag + "_src"].astype(np.float32), g[tag + "_trg"].astype(np.float32)
+    got, _ = gpu_mix(R, src[None], trg[None], [0], [int(k)], float(L), O.PROSTATE_EPILOGUE)
+    want = O.epilogue(g[tag + "_out"].astype(np.float64).transpose(2, 0, 1), *O.PROSTATE_EPILOGUE)
+    check(got[0], want, "prostate384 " + tag)
+
+
+def test_golden_known_answers(R, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ram_kats.npz"))
+    none = (-math.inf, math.inf, 1.0, 0.0)
+    # ratio == 1.0: delta is multiplied by (10 - 10) / 10 == 0 -> output is the input, bit for bit
+    src = g["ratio1_src"]
+    got, _ = gpu_mix(R, src[None], g["ratio1_trg"][None], [0], [10], 0.1, none)
+    np.testing.assert_array_equal(got[0], src)
+    # partner == source: identity within tolerance for any ratio
+    got, _ = gpu_mix(R, g["same_src"][None], g["same_src"][None], [0], [int(g["same_k"])], 0.1, O.FUNDUS_EPILOGUE)
+    check(got[0], O.epilogue(g["same_out"].transpose(2, 0, 1), *O.FUNDUS_EPILOGUE), "same")
+    # all-zero source: zero-amplitude bins take phase 0
+    zero = np.zeros_like(src)
+    got, _ = gpu_mix(R, zero[None], g["zero_trg"][None], [0], [int(g["zero_k"])], 0.1, O.FUNDUS_EPILOGUE)
+    check(got[0], O.epilogue(g["zero_out"].transpose(2, 0, 1), *O.FUNDUS_EPILOGUE), "zero source")
+    # b == 0: only DC changes
+    got, _ = gpu_mix(R, g["dc_src"][None], g["dc_trg"][None], [0], [int(g["dc_k"])], 0.01, O.FUNDUS_EPILOGUE)
+    check(got[0], O.epilogue(g["dc_out"].transpose(2, 0, 1), *O.FUNDUS_EPILOGUE), "b == 0")
+
+
+# ------------------------------------------------------------------------------------------------
+# (2) seeded oracle parity
+def _smooth(rs, shape, lo, hi, integer):
+    n, c, h, w = shape
+    z = rs.standard_normal(shape)
+    fy = np.fft.fftfreq(h)[:, None]
+    fx = np.fft.fftfreq(w)[None, :]
+    y = np.real(np.fft.ifft2(np.fft.fft2(z) / (1.0 + (np.hypot(fy, fx) / 0.05) ** 2)))
+    y = (y - y.min()) / (y.max() - y.min())
+    y = lo + (hi - lo) * y
+    return (np.round(y) if integer else y).astype(np.float32)
+
+
+SHAPES = [  # (C, H, W, L, integer-valued?)
+    (3, 256, 256, 0.1, True),     # fundus, fused
+    (1, 384, 384, 0.1, False),    # prostate-shaped, fused (H = 16 * 24)
+    (3, 384, 384, 0.1, False),    # real prostate layout
+    (2, 64, 128, 0.1, True),      # non-square, fused
+    (1, 128, 64, 0.05, False),
+    (1, 512, 256, 0.1, True),
+    (3, 31, 45, 0.1, True),       # odd, generic
+    (2, 33, 33, 0.2, True),
+    (1, 100, 60, 0.1, False),     # even, not multiples of 16/64: generic
+    (1, 48, 40, 0.1, False),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "%dx%dx%d_L%g" % s[:4])
+def test_oracle_parity_all_ratios(R, shape):
+    c, h, w, L, integer = shape
+    rs = np.random.RandomState(h * 1000 + w)
+    lo, hi = (0, 255) if integer else (-1, 1)
+    nsrc, npar = 10, 4
+    src = _smooth(rs, (nsrc, c, h, w), lo, hi, integer)
+    par = _smooth(rs, (npar, c, h, w), lo, hi, integer)
+    rk = np.arange(1, 11, dtype=np.int32)                  # every ratio the reference can draw
+    pidx = rs.randint(0, npar, size=nsrc).astype(np.int64)
+    epi = O.FUNDUS_EPILOGUE if integer else O.PROSTATE_EPILOGUE
+    got, bank = gpu_mix(R, src, par, pidx, rk, L, epi)
+    want = O.mix_batch(src, par, pidx, rk, L, epi=epi)
+    check(got, want, str(shape))
+    want_bank = O.build_bank(par, L)
+    assert bank.shape == want_bank.shape
+    assert O.rel_l2(bank, want_bank) <= 1e-6
+
+
+def test_white_noise_inputs(R):
+    """Flat spectra (white noise): every band bin has a comparable, small amplitude."""
+    rs = np.random.RandomState(5)
+    src = rs.randint(0, 256, (4, 3, 256, 256)).astype(np.float32)
+    par = rs.randint(0, 256, (3, 3, 256, 256)).astype(np.float32)
+    pidx, rk = np.array([0, 1, 2, 1]), np.array([3, 7, 1, 5], np.int32)
+    got, _ = gpu_mix(R, src, par, pidx, rk, 0.1, O.FUNDUS_EPILOGUE)
+    want = O.mix_batch(src, par, pidx, rk, 0.1, epi=O.FUNDUS_EPILOGUE)
+    check(got, want, "white noise")
+
+
+def test_generic_and_fused_paths_agree(R):
+    rs = np.random.RandomState(9)
+    src = _smooth(rs, (6, 3, 256, 256), 0, 255, True)
+    par = _smooth(rs, (3, 3, 256, 256), 0, 255, True)
+    pidx, rk = rs.randint(0, 3, 6), rs.randint(1, 10, 6).astype(np.int32)
+    a, bank_a = gpu_mix(R, src, par, pidx, rk, 0.1, O.FUNDUS_EPILOGUE)
+    g, bank_g = gpu_mix(R, src, par, pidx, rk, 0.1, O.FUNDUS_EPILOGUE, force_generic=True)
+    check(a, g, "fused vs generic")
+    assert O.rel_l2(bank_a, bank_g) <= 1e-6
+
+
+def test_arbitrary_amp_trg_is_symmetrised_exactly(R):
+    """source_to_target_freq accepts ANY amp_trg array; Re(ifft2) then only sees its +-k average."""
+    rs = np.random.RandomState(11)
+    src = _smooth(rs, (1, 2, 64, 64), 0, 255, True)[0]
+    amp = np.abs(rs.standard_normal((2, 64, 64))) * 1e4      # not the spectrum of any real image
+    random.seed(3)
+    k = random.randint(1, 10)
+    want = O.mix_sample(src.transpose(1, 2, 0), amp, L=0.1, ratio=k / 10)
+    random.seed(3)
+    got = R.source_to_target_freq(src.transpose(1, 2, 0), amp.astype(np.float32), L=0.1)
+    assert got.shape == want.shape
+    assert O.rel_l2(got, want) <= REL_L2_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# per-sample drop-in API
+def test_dropin_functions_match_golden(R, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ram_small.npz"))
+    for key in ("sq32_0", "odd31x45_0", "rect48x40_0"):
+        L, k = g[key + "_meta"]
+        src, trg = g[key + "_src"], g[key + "_trg"]
+        amp = R.extract_amp_spectrum(trg)
+        assert amp.shape == trg.shape and amp.dtype == np.float32
+        assert O.rel_l2(amp, g[key + "_amp"]) <= 1e-6
+        # same seed the fixture used -> the shim draws the same ratio from the global `random`
+        idx = list(g["names"]).index(key)
+        random.seed(1000 + 10 * (idx // 2) + (idx % 2))
+        out = R.source_to_target_freq(src.transpose(1, 2, 0), amp, L=float(L))
+        state_after = random.getstate()
+        random.seed(1000 + 10 * (idx // 2) + (idx % 2))
+        assert random.randint(1, 10) == int(k)
+        assert random.getstate() == state_after            # exactly ONE draw was consumed (fundus.py:35)
+        assert out.shape == g[key + "_out"].shape
+        assert O.rel_l2(out, g[key + "_out"]) <= REL_L2_TOL
+        unit = 127.5 if float(np.abs(src).max()) > 2.0 else 1.0      # intensity units per normalised unit
+        assert O.max_abs(out, g[key + "_out"]) / unit <= MAX_ABS_TOL
+        # float64 in -> float64 out (numpy-1.x precision class)
+        assert R.source_to_target_freq(src.transpose(1, 2, 0).astype(np.float64), amp, L=float(L)).dtype == np.float64
+
+
+def test_dropin_low_freq_mutate(R):
+    rs = np.random.RandomState(2)
+    for (c, h, w, L) in ((3, 32, 32, 0.1), (2, 31, 45, 0.1), (1, 64, 48, 0.2)):
+        a_s = np.abs(rs.standard_normal((c, h, w))).astype(np.float32) * 100
+        a_t = np.abs(rs.standard_normal((c, h, w))).astype(np.float32) * 100
+        keep_s, keep_t = a_s.copy(), a_t.copy()
+        random.seed(42)
+        k = random.randint(1, 10)
+        random.seed(42)
+        got = R.low_freq_mutate_np(a_s, a_t, L=L)
+        want = O.blend_low_band(a_s.astype(np.float64), a_t.astype(np.float64), L, k / 10)
+        np.testing.assert_allclose(got, want, rtol=2e-7, atol=1e-5)
+        np.testing.assert_array_equal(a_s, keep_s)          # inputs are not mutated
+        np.testing.assert_array_equal(a_t, keep_t)
+        # outside the band the source amplitude is returned untouched
+        h1, h2, w1, w2 = O.band_window(h, w, L)
+        mask = np.ones((c, h, w), bool)
+        mask[:, h1:h2, w1:w2] = False
+        mask = np.fft.ifftshift(mask, axes=(-2, -1))
+        np.testing.assert_array_equal(got[mask], a_s[mask])
+
+
+def test_shape_mismatch_raises(R):
+    with pytest.raises(ValueError):
+        R.source_to_target_freq(np.zeros((32, 32, 3), np.float32), np.zeros((3, 16, 16), np.float32))
+    with pytest.raises(ValueError):
+        R.low_freq_mutate_np(np.zeros((3, 32, 32), np.float32), np.zeros((3, 32, 16), np.float32))
+    src = torch.zeros(2, 3, 64, 64, device="cuda")
+    bank = torch.zeros(4, 3, 13, 13, device="cuda")
+    with pytest.raises(ValueError):
+        R.ram_mix_batch(src, bank, [0, 4], [5, 5])           # partner index outside the bank
+    with pytest.raises(ValueError):
+        R.ram_mix_batch(src, torch.zeros(4, 3, 11, 11, device="cuda"), [0, 1], [5, 5])
+    with pytest.raises(ValueError):
+        R.ram_mix_batch(src, bank, [0, 1], [5, 5], out=src)  # in place is refused
+    with pytest.raises(Exception):
+        R.ram_mix_batch(torch.zeros(1, 1, 64, 64, device="cuda"), torch.zeros(1, 1, 65, 65, device="cuda"), [0], [5], L=0.5)
+
+
+def test_device_side_bad_partner_poisons_with_nan(R):
+    src = torch.rand(2, 1, 64, 64, device="cuda")
+    bank = R.build_amp_bank(torch.rand(3, 1, 64, 64, device="cuda"))
+    pidx = torch.tensor([1, 99], device="cuda")              # device tensors cannot be validated on the host
+    out = R.ram_mix_batch(src, bank, pidx, torch.tensor([5, 5], dtype=torch.int32, device="cuda"))
+    assert torch.isfinite(out[0]).all() and torch.isnan(out[1]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# (3) full BASELINE sizes: size-independent properties
+def _amp_identity(R, B, C, H, W, nbank, seed):
+    """bank(RAM(x)) == ratio * bank(x) + (1 - ratio) * bank(partner) on the band (no clipping)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    src = torch.rand(B, C, H, W, device="cuda", generator=g) * 255.0
+    par = torch.rand(nbank, C, H, W, device="cuda", generator=g) * 255.0
+    bank = R.build_amp_bank(par)
+    rs = np.random.RandomState(seed)
+    pidx = torch.from_numpy(rs.randint(0, nbank, B)).cuda()
+    rk = torch.from_numpy(rs.randint(1, 11, B).astype(np.int32)).cuda()
+    out = R.ram_mix_batch(src, bank, pidx, rk)
+    a_src, a_out = R.build_amp_bank(src), R.build_amp_bank(out)
+    r = (rk.float() / 10).view(B, 1, 1, 1)
+    want = r * a_src + (1 - r) * bank[pidx]
+    rel = (a_out - want).norm() / want.norm()
+    assert rel.item() <= 2e-6, rel.item()
+    # ratio == 10/10 rows are returned bit-identical
+    same = (rk == 10).nonzero().flatten()
+    if same.numel():
+        assert torch.equal(out[same], src[same])
+    # the result is independent of the batch it is computed in (each image alone == in the batch)
+    i = B // 2
+    alone = R.ram_mix_batch(src[i:i + 1].contiguous(), bank, pidx[i:i + 1], rk[i:i + 1])
+    assert torch.equal(alone[0], out[i])
+    return out
+
+
+def test_full_size_fundus_batch(R):
+    _amp_identity(R, 256, 3, 256, 256, 64, 1337)            # BASELINE config 2
+
+
+def test_full_size_prostate_batch(R):
+    _amp_identity(R, 512, 1, 384, 384, 64, 1338)            # BASELINE config 3
+
+
+def test_hires_1024(R):
+    _amp_identity(R, 4, 3, 1024, 1024, 3, 1339)             # BASELINE config 5 shape (reduced batch)
+
+
+def test_host_pipeline_matches_device_path(R):
+    """ramdsir_mix_host_f32 (pinned host buffers, chunked H2D/compute/D2H) == ram_mix_batch bit for bit."""
+    from ramdsir_b200.host import HostPipeline
+    rs = np.random.RandomState(3)
+    B, C, H, W, nbank = 37, 3, 256, 256, 5                   # ragged: not a multiple of the chunk
+    src = torch.from_numpy(rs.randint(0, 256, (B, C, H, W)).astype(np.float32)).pin_memory()
+    bank = R.build_amp_bank(torch.from_numpy(rs.randint(0, 256, (nbank, C, H, W)).astype(np.float32)).cuda())
+    pidx = rs.randint(0, nbank, B).astype(np.int64)
+    rk = rs.randint(1, 11, B).astype(np.int32)
+    out = torch.empty_like(src).pin_memory()
+    with HostPipeline(chunk_images=8, C=C, H=H, W=W) as pipe:
+        pipe.mix(src, bank, pidx, rk, out, epilogue=O.FUNDUS_EPILOGUE)
+        want = R.ram_mix_batch(src.cuda(), bank, pidx, rk, clip=(0.0, 255.0), scale=1 / 127.5, shift=-1.0).cpu()
+        assert torch.equal(out, want)
+        with pytest.raises(Exception):
+            pipe.mix(src, bank, np.full(B, nbank), rk, out)  # out-of-range partner index is refused on the host
+    empty = torch.empty(0, C, H, W, device="cuda")
+    assert R.ram_mix_batch(empty, bank, [], []).shape == (0, C, H, W)

@@ -1,0 +1,80 @@
+// CPU emulation of the fused RAM kernel's CTA pipeline (TEST TOOL, never shipped or imported by
+// the package): runs the exact __host__ __device__ phase bodies of ram_fused_core.cuh task by
+// task, with a heap buffer standing in for shared memory, so the index algebra can be checked
+// against the numpy oracle in a container without a GPU.
+//   g++ -O2 -shared -fPIC -I ramdsir_b200/csrc tools/emulate/emul_fused.cpp -o tools/emulate/libemul.so
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "ram_fused_host.h"
+
+using namespace ramdsir;
+
+template <int MMAX>
+static void run_plane(const FusedShape& S, unsigned char* sm, const float* x, const float* patch,
+                      float omr, float* y, Epilogue ep, float* bank_out) {
+  auto ld = [&](size_t off) { const float* p = x + 4 * off; return make_float4(p[0], p[1], p[2], p[3]); };
+  auto st = [&](size_t off, float4 v) { float* p = y + 4 * off; p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; };
+  const int NT = S.nthreads;
+  std::vector<cf> regs((size_t)NT * 32);
+  for (int strip = 0; strip < S.nstrips; ++strip) {
+    for (int t = 0; t < NT; ++t) {
+      cf(&va)[16] = *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]);
+      cf(&vb)[16] = *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32 + 16]);
+      f1_load_fft(S, ld, strip, t, va, vb);
+    }
+    for (int half = 0; half < 2; ++half) {
+      for (int t = 0; t < NT; ++t) {
+        cf(&va)[16] = *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]);
+        cf(&vb)[16] = *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32 + 16]);
+        f1_store_half(S, sm, t, half, va, vb);
+      }
+      for (int u = 0; u < 256; ++u) f1_direct<MMAX>(S, sm, strip, half, u);
+    }
+  }
+  for (int r = 0; r < S.nb * S.N1w; ++r) row_fwd(S, sm, r);
+  if (bank_out) {
+    for (int q = 0; q < S.nb * (S.b + 1); ++q) band_amp(S, sm, bank_out, q);
+    return;
+  }
+  for (int q = 0; q < S.nb * (S.b + 1); ++q) band_mix(S, sm, patch, omr, q);
+  for (int r = 0; r < S.nb * S.N1w; ++r) row_inv<MMAX>(S, sm, r);
+  for (int strip = 0; strip < S.nstrips; ++strip)
+    for (int t = 0; t < NT; ++t) col_inv_store<MMAX>(S, sm, ld, st, ep, strip, t);
+}
+
+template <int MMAX>
+static int run_all(const FusedShape& S, const float* src, const float* bank, const long long* pidx,
+                   const int* rk, int den, float* out, int B, int C, Epilogue ep, float* bank_out) {
+  std::vector<unsigned char> sm(S.smemBytes);
+  fused_tables_fill(S, reinterpret_cast<float*>(sm.data() + S.offTab));
+  const size_t plane = (size_t)S.H * S.W, psz = (size_t)S.nb * S.nb;
+  for (int i = 0; i < B; ++i)
+    for (int c = 0; c < C; ++c) {
+      const size_t p = (size_t)i * C + c;
+      if (bank_out) { run_plane<MMAX>(S, sm.data(), src + p * plane, nullptr, 0.f, nullptr, ep, bank_out + p * psz); continue; }
+      const float omr = (float)(den - rk[i]) / (float)den;
+      run_plane<MMAX>(S, sm.data(), src + p * plane, bank + ((size_t)pidx[i] * C + c) * psz, omr, out + p * plane, ep, nullptr);
+    }
+  return 0;
+}
+
+extern "C" int emul_fused(const float* src, const float* bank, const long long* pidx, const int* rk, int den,
+                          float* out, int B, int C, int H, int W, int b, float lo, float hi, float scale,
+                          float shift, float* bank_out) {
+  FusedShape S;
+  if (!fused_shape_init(S, H, W, b)) return 1;
+  Epilogue ep{lo, hi, scale, shift};
+  switch (S.MM) {
+    case 0: case 1: return run_all<1>(S, src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+    case 2: return run_all<2>(S, src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+    case 3: return run_all<3>(S, src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+    case 4: return run_all<4>(S, src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+  }
+  return 2;
+}
+
+extern "C" int emul_fused_smem_bytes(int H, int W, int b) {
+  FusedShape S;
+  return fused_shape_init(S, H, W, b) ? S.smemBytes : -1;
+}
