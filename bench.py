@@ -33,11 +33,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED = 1337                       # reference default (train.py:60)
-C, H, W, L = 3, 256, 256, 0.1
+L = 0.1
+# BASELINE.json configs[1] is the headline (default); the others are selectable for development runs.
+WORKLOADS = {
+    "fundus": dict(C=3, H=256, W=256, BATCH=256, N_BANK=768, N_DOMAINS=3, EPI="fundus", LO=0, HI=256,
+                   NAME="fundus RAM batch 256x3x256x256 fp32, L=0.1 (b=25), 3 source domains, clip[0,255]/127.5-1"),
+    "prostate": dict(C=1, H=384, W=384, BATCH=512, N_BANK=640, N_DOMAINS=5, EPI="prostate", LO=-1, HI=1,
+                     NAME="prostate RAM batch 512x1x384x384 fp32, L=0.1 (b=38), 5 source domains, clip[-1,1]"),
+    "prostate3": dict(C=3, H=384, W=384, BATCH=128, N_BANK=320, N_DOMAINS=5, EPI="prostate", LO=-1, HI=1,
+                      NAME="prostate RAM batch 128x3x384x384 fp32 (real 3-slice layout), L=0.1 (b=38), clip[-1,1]"),
+    "hires": dict(C=3, H=1024, W=1024, BATCH=64, N_BANK=48, N_DOMAINS=3, EPI="fundus", LO=0, HI=256,
+                  NAME="high-res fundus RAM batch 64x3x1024x1024 fp32, L=0.1 (b=102), clip[0,255]/127.5-1"),
+}
+C, H, W = 3, 256, 256
 BATCH = 256                       # per GPU (configs[1])
 N_BANK = 768                      # source images in the amplitude bank (3 domains x 256; real fundus: 789)
 N_DOMAINS = 3
-WORKLOAD = "fundus RAM batch 256x3x256x256 fp32, L=0.1 (b=25), 3 source domains, clip[0,255]/127.5-1"
+EPI_NAME, LO, HI = "fundus", 0, 256
+WORKLOAD = WORKLOADS["fundus"]["NAME"]
+
+
+def select_workload(name):
+    global C, H, W, BATCH, N_BANK, N_DOMAINS, WORKLOAD, EPI_NAME, LO, HI
+    w = WORKLOADS[name]
+    C, H, W, BATCH, N_BANK, N_DOMAINS = w["C"], w["H"], w["W"], w["BATCH"], w["N_BANK"], w["N_DOMAINS"]
+    WORKLOAD, EPI_NAME, LO, HI = w["NAME"], w["EPI"], w["LO"], w["HI"]
+
+
+def synth(torch, shape, dev, gen):
+    """Synthetic images: uint8-valued floats for fundus (fundus.py:212), uniform [-1, 1] for prostate."""
+    if EPI_NAME == "fundus":
+        return torch.randint(0, 256, shape, device=dev, generator=gen).float()
+    return torch.rand(shape, device=dev, generator=gen) * 2.0 - 1.0
 
 
 def algorithmic_bytes_per_image(c, h, w, b):
@@ -74,8 +101,13 @@ def _cpu_init(seed):
     from oracle import ram_oracle as O
     rs = np.random.RandomState(seed)
     _CPU["O"] = O
-    _CPU["src"] = rs.randint(0, 256, (8, C, H, W)).astype(np.float32)
-    _CPU["par"] = rs.randint(0, 256, (8, C, H, W)).astype(np.float32)
+    if EPI_NAME == "fundus":
+        _CPU["src"] = rs.randint(0, 256, (8, C, H, W)).astype(np.float32)
+        _CPU["par"] = rs.randint(0, 256, (8, C, H, W)).astype(np.float32)
+    else:
+        _CPU["src"] = (rs.rand(8, C, H, W) * 2 - 1).astype(np.float32)
+        _CPU["par"] = (rs.rand(8, C, H, W) * 2 - 1).astype(np.float32)
+    _CPU["epi"] = O.FUNDUS_EPILOGUE if EPI_NAME == "fundus" else O.PROSTATE_EPILOGUE
 
 
 def _cpu_work(args):
@@ -83,7 +115,7 @@ def _cpu_work(args):
     mix, clip, normalise.  float64 path (= numpy 1.x behaviour, the parity oracle)."""
     i, pidx, rk = args
     O = _CPU["O"]
-    y = O.mix_batch(_CPU["src"][i % 8][None], _CPU["par"], [pidx % 8], [rk], L, epi=O.FUNDUS_EPILOGUE)
+    y = O.mix_batch(_CPU["src"][i % 8][None], _CPU["par"], [pidx % 8], [rk], L, epi=_CPU["epi"])
     return float(y[0, 0, 0, 0])
 
 
@@ -224,7 +256,7 @@ def run_ours(args, rank, local_rank, world):
 
     b = R.band_halfwidth(H, W, L)
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
-    src = torch.randint(0, 256, (BATCH, C, H, W), device=dev, generator=g).float()
+    src = synth(torch, (BATCH, C, H, W), dev, g)
     out = torch.empty_like(src)
 
     # amplitude bank: built sharded (each rank its rows), replicated once by an all-gather
@@ -232,7 +264,7 @@ def run_ours(args, rank, local_rank, world):
     gb = torch.Generator(device=dev).manual_seed(SEED * 7 + 1)
     bank_src_all = None
     torch.cuda.synchronize()
-    bank_imgs = torch.randint(0, 256, (hi - lo, C, H, W), device=dev, generator=gb).float()
+    bank_imgs = synth(torch, (hi - lo, C, H, W), dev, gb)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
@@ -246,7 +278,7 @@ def run_ours(args, rank, local_rank, world):
 
     pidx_h, rk_h = draw_selection(BATCH, N_BANK, SEED + rank)
     pidx, rk = torch.from_numpy(pidx_h).to(dev), torch.from_numpy(rk_h).to(dev)
-    epi = R.FUNDUS_EPILOGUE
+    epi = R.FUNDUS_EPILOGUE if EPI_NAME == "fundus" else R.PROSTATE_EPILOGUE
 
     def step():
         R.ram_mix_batch(src, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=out)
@@ -278,8 +310,8 @@ def run_ours(args, rank, local_rank, world):
     # end-to-end through the host-buffer C-ABI entry (pinned host -> device -> pinned host)
     src_h = src.cpu().pin_memory()
     out_h = torch.empty_like(src_h).pin_memory()
-    e2e_steps = max(3, min(args.steps, 30))
-    with HostPipeline(chunk_images=32, C=C, H=H, W=W, L=L) as pipe:
+    e2e_steps = 1 if args.no_e2e else max(3, min(args.steps, 30))
+    with HostPipeline(chunk_images=max(1, BATCH // 8), C=C, H=H, W=W, L=L) as pipe:
         for _ in range(3):
             pipe.mix(src_h, bank, pidx_h, rk_h, out_h, epilogue=epi)
         if world > 1:
@@ -307,7 +339,8 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "bank_images": N_BANK,
                        "bank_build_allgather_ms": bank_ms, "seed": SEED,
-                       "l2": "inputs 201 MB + outputs 201 MB per step exceed the 126 MB L2 (no flush needed)",
+                       "l2": "inputs %.0f MB + outputs %.0f MB per step exceed the 126 MB L2 (no flush needed)"
+                             % (src.numel() * 4 / 1e6, src.numel() * 4 / 1e6),
                        "parallelism": "batch-sharded x%d, bank all-gather once" % world,
                        "kernel_path": {1: "fused", 2: "multipass", 3: "generic"}.get(R.kernel_path(C, H, W, b))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -341,7 +374,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="(dev) shorten the host-buffer end-to-end leg to one step")
+    ap.add_argument("--workload", default="fundus", choices=sorted(WORKLOADS), help="(dev) default = BASELINE configs[1]")
     args = ap.parse_args()
+    select_workload(args.workload)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -73,12 +73,137 @@ ram_fused_kernel(const FusedShape S, const float* __restrict__ src, const float*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Static-shape kernel (ram_fused_static.cuh): the BASELINE shapes.  Two CTAs per SM for 256^2.
+//
+// Memory-system choreography.  A plane is read twice (forward columns, then y = x + delta), and the
+// second read must come from L2, not HBM, for DRAM traffic to stay at the algorithmic 2 * plane bytes:
+//   * first read:  ld.global.nc with L2::evict_last  -> keep x resident while the band is processed
+//   * second read: L2::evict_first                   -> the line is dead after this use
+//   * output:      st.global with L2::evict_first    -> streaming stores must not displace x
+//   * the second pass walks the column strips in REVERSE order (most recently read strip first)
+//   * while a strip is being processed, the next strip's lines are prefetched into L2.
+__device__ __forceinline__ float4 ldg_policy(const float4* p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_policy(float4* p, float4 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// Each thread prefetches 2 of the 128-byte lines its warp will load for column strip `strip`:
+// a warp covers rows (h1w + (lane >> 4)) + N1h * (lane & 15), 256 bytes (2 lines) each.
+template <class CFG>
+__device__ __forceinline__ void prefetch_strip(const float4* x4, int strip, int tid) {
+  const int lane = tid & 31, h1w = (tid >> 5) * 2;
+  const int row = h1w + (lane >> 4) + CFG::N1h * (lane & 15);
+  const float4* p = x4 + (size_t)row * CFG::M + strip * 16;
+  prefetch_l2(p);
+  prefetch_l2(p + 8);
+}
+
+template <class CFG, bool BANK>
+__global__ void __launch_bounds__(CFG::nthreads, (CFG::smemBytes <= 113 * 1024) ? 2 : 1)
+ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__ bank,
+                        const int64_t* __restrict__ pidx, const int32_t* __restrict__ rk, int ratio_den, int n_bank,
+                        int C, float* __restrict__ out, const Epilogue ep, const float* __restrict__ tables, int nplanes) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  constexpr int NT = CFG::nthreads;
+  const int tid = threadIdx.x;
+  unsigned long long pol_keep, pol_stream;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  {
+    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
+    const float4* g = reinterpret_cast<const float4*>(tables);
+    for (int i = tid; i < CFG::tabBytes / 16; i += NT) tab[i] = g[i];
+  }
+  __syncthreads();
+  constexpr size_t plane_px = (size_t)CFG::H * CFG::W;
+  constexpr size_t patch_px = (size_t)CFG::nb * CFG::nb;
+  for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
+    const float4* x4 = reinterpret_cast<const float4*>(src + plane * plane_px);
+    auto ld_first = [&](size_t off) { return BANK ? __ldg(x4 + off) : ldg_policy(x4 + off, pol_keep); };
+    // ---- forward columns ----
+    for (int strip = 0; strip < CFG::nstrips; ++strip) {
+      cf va[16], vb[16];
+      s_f1_load_fft_tw<CFG>(ld_first, sm, strip, tid, va, vb);
+      if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        s_f1_store_half<CFG>(sm, tid, half, va, vb);
+        __syncthreads();
+        for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, half, u);
+        __syncthreads();
+      }
+    }
+    // ---- forward rows on the band rows; meanwhile stage the partner patch / prefetch the next plane ----
+    Epilogue epp = ep;
+    float omr = 0.f;
+    if (!BANK) {
+      const int img = plane / C, ch = plane - img * C;
+      const long long p = pidx[img];
+      const bool ok = (p >= 0 && p < (long long)n_bank);
+      if (!ok) epp.scale = __int_as_float(0x7fc00000);   // poison the plane (fminf/fmaxf swallow a NaN delta)
+      omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
+      const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
+      for (int i = tid; i < (int)patch_px; i += NT) s_stage_patch<CFG>(sm, patch, i);
+    }
+    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) s_row_fwd<CFG>(sm, r);
+    __syncthreads();
+    if (BANK) {
+      float* patch = out + plane * patch_px;
+      for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) s_band_amp<CFG>(sm, patch, q);
+      __syncthreads();
+      continue;
+    }
+    for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) s_band_mix<CFG>(sm, omr, q);
+    __syncthreads();
+    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) s_row_inv<CFG>(sm, r);
+    __syncthreads();
+    // ---- inverse columns + x + epilogue, strips in reverse order ----
+    {
+      float4* y4 = reinterpret_cast<float4*>(out + plane * plane_px);
+      auto ld_again = [&](size_t off) { return ldg_policy(x4 + off, pol_stream); };
+      auto st = [&](size_t off, float4 v) { stg_policy(y4 + off, v, pol_stream); };
+      const int next = plane + gridDim.x;
+      for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
+        cf eva[8], evb[8], oda[8], odb[8];
+        if (strip > 0) prefetch_strip<CFG>(x4, strip - 1, tid);
+        else if (next < nplanes) prefetch_strip<CFG>(reinterpret_cast<const float4*>(src + next * plane_px), 0, tid);
+        for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 0, u);
+        __syncthreads();
+        s_inv_fft8<CFG>(sm, tid, 0, eva, evb);
+        __syncthreads();
+        for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 1, u);
+        __syncthreads();
+        s_inv_fft8<CFG>(sm, tid, 1, oda, odb);
+        __syncthreads();
+        s_inv_combine_store<CFG>(ld_again, st, epp, strip, tid, eva, evb, oda, odb);
+      }
+    }
+    // next plane: its first E write happens after its loads and Z is only rewritten two barriers later
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 namespace {
 struct FusedPlan {
   FusedShape S;
   float* tables = nullptr;  // device
   int sm_count = 0;
+  int static_id = 0;        // 0: runtime-shape kernel; 1: SCfg<256,256,25>; 2: SCfg<384,384,38>
 };
+using Cfg256 = SCfg<256, 256, 25>;
+using Cfg384 = SCfg<384, 384, 38>;
+int static_id_of(int H, int W, int b) {
+  if (H == 256 && W == 256 && b == 25) return 1;
+  if (H == 384 && W == 384 && b == 38) return 2;
+  return 0;
+}
 std::mutex g_mu;
 std::map<std::tuple<int, int, int, int>, FusedPlan> g_plans;  // (device, H, W, b)
 
@@ -94,10 +219,14 @@ int get_plan(int H, int W, int b, FusedPlan** out) {
       set_error("fused path does not support H=%d W=%d b=%d", H, W, b);
       return RAMDSIR_ERR_UNSUPPORTED;
     }
-    std::vector<float> host(p.S.tabBytes / 4);
-    fused_tables_fill(p.S, host.data());
-    RD_CUDA(cudaMalloc(&p.tables, p.S.tabBytes));
-    RD_CUDA(cudaMemcpy(p.tables, host.data(), p.S.tabBytes, cudaMemcpyHostToDevice));
+    p.static_id = static_id_of(H, W, b);
+    const int tab_bytes = p.static_id == 1 ? Cfg256::tabBytes : p.static_id == 2 ? Cfg384::tabBytes : p.S.tabBytes;
+    std::vector<float> host(tab_bytes / 4);
+    if (p.static_id == 1) fused_tables_fill_static<Cfg256>(host.data());
+    else if (p.static_id == 2) fused_tables_fill_static<Cfg384>(host.data());
+    else fused_tables_fill(p.S, host.data());
+    RD_CUDA(cudaMalloc(&p.tables, tab_bytes));
+    RD_CUDA(cudaMemcpy(p.tables, host.data(), tab_bytes, cudaMemcpyHostToDevice));
     RD_CUDA(cudaDeviceSynchronize());  // once per shape: tables are visible to every stream afterwards
     RD_CUDA(cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev));
     it = g_plans.emplace(key, p).first;
@@ -126,9 +255,29 @@ int launch(const FusedPlan& p, const float* src, const float* bank, const int64_
   return RAMDSIR_OK;
 }
 
+template <class CFG, bool BANK>
+int launch_static(const FusedPlan& p, const float* src, const float* bank, const int64_t* pidx, const int32_t* rk,
+                  int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
+  auto kern = ram_fused_static_kernel<CFG, BANK>;
+  static thread_local int per_sm = 0;  // per instantiation
+  if (per_sm == 0) {
+    RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
+    RD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::nthreads, CFG::smemBytes));
+    if (per_sm < 1) per_sm = 1;
+  }
+  int grid = p.sm_count * per_sm;
+  if (grid > nplanes) grid = nplanes;
+  kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes);
+  count_launch();
+  RD_CUDA(cudaGetLastError());
+  return RAMDSIR_OK;
+}
+
 template <bool BANK>
 int dispatch(const FusedPlan& p, const float* src, const float* bank, const int64_t* pidx, const int32_t* rk,
              int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
+  if (p.static_id == 1) return launch_static<Cfg256, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
+  if (p.static_id == 2) return launch_static<Cfg384, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
   switch (p.S.MM) {
     case 0:
     case 1: return launch<1, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);

@@ -51,17 +51,21 @@ static inline float4 make_float4(float a, float b, float c, float d) { return fl
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 #endif
 
-RD_HD float4* smemZ(const FusedShape& S, unsigned char* sm) { return reinterpret_cast<float4*>(sm + S.offZ); }
-RD_HD float4* smemE(const FusedShape& S, unsigned char* sm) { return reinterpret_cast<float4*>(sm + S.offE); }
-RD_HD float2* smemD(const FusedShape& S, unsigned char* sm) { return reinterpret_cast<float2*>(sm + S.offD); }
-RD_HD const float* smemTab(const FusedShape& S, const unsigned char* sm) { return reinterpret_cast<const float*>(sm + S.offTab); }
+template <class SH>
+RD_HD float4* smemZ(const SH& S, unsigned char* sm) { return reinterpret_cast<float4*>(sm + S.offZ); }
+template <class SH>
+RD_HD float4* smemE(const SH& S, unsigned char* sm) { return reinterpret_cast<float4*>(sm + S.offE); }
+template <class SH>
+RD_HD float2* smemD(const SH& S, unsigned char* sm) { return reinterpret_cast<float2*>(sm + S.offD); }
+template <class SH>
+RD_HD const float* smemTab(const SH& S, const unsigned char* sm) { return reinterpret_cast<const float*>(sm + S.offTab); }
 RD_HD cf ldcf(const float* p) { return cf{p[0], p[1]}; }
 
 // ---------------------------------------------------------------------------------------------
 // F1a: task t = (h1 = t / 16, c = t % 16) of column strip `strip`: load rows h1 + N1h * j,
 // radix-16 forward over j for both packed columns.
-template <class LoadF4>
-RD_HD void f1_load_fft(const FusedShape& S, LoadF4 ld, int strip, int t, cf (&va)[16], cf (&vb)[16]) {
+template <class SH, class LoadF4>
+RD_HD void f1_load_fft(const SH& S, LoadF4 ld, int strip, int t, cf (&va)[16], cf (&vb)[16]) {
   const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -74,7 +78,8 @@ RD_HD void f1_load_fft(const FusedShape& S, LoadF4 ld, int strip, int t, cf (&va
 }
 
 // F1b: publish k2 in [8*half, 8*half+8) to E[k2l][h1][c] as (a.re, a.im, b.re, b.im).
-RD_HD void f1_store_half(const FusedShape& S, unsigned char* sm, int t, int half, const cf (&va)[16], const cf (&vb)[16]) {
+template <class SH>
+RD_HD void f1_store_half(const SH& S, unsigned char* sm, int t, int half, const cf (&va)[16], const cf (&vb)[16]) {
   float4* E = smemE(S, sm);
   const int h1 = t >> 4, c = t & 15;
 #pragma unroll
@@ -88,8 +93,8 @@ RD_HD void f1_store_half(const FusedShape& S, unsigned char* sm, int t, int half
 
 // F1c: task u in [0, 256): col = u & 1, c = (u >> 1) & 15, k2l = u >> 5.
 // Z[kh][strip*16 + c].col = sum_h1 W_H^(h1 kh) * E[k2l][h1][c].col for every band row kh = k2 (mod 16).
-template <int MMAX>
-RD_HD void f1_direct(const FusedShape& S, unsigned char* sm, int strip, int half, int u) {
+template <int MMAX, class SH>
+RD_HD void f1_direct(const SH& S, unsigned char* sm, int strip, int half, int u) {
   const float2* E2 = reinterpret_cast<const float2*>(smemE(S, sm));
   float2* Z2 = reinterpret_cast<float2*>(smemZ(S, sm));
   const float* tw1 = smemTab(S, sm) + S.tTW1;
@@ -117,7 +122,8 @@ RD_HD void f1_direct(const FusedShape& S, unsigned char* sm, int strip, int half
 // ---------------------------------------------------------------------------------------------
 // Row forward, in place on Z: task r = (khi = r / N1w, c1 = r % N1w); radix-16 over j for the
 // elements c1 + N1w * j; X[k2] is written back to slot c1 + N1w * k2.
-RD_HD void row_fwd(const FusedShape& S, unsigned char* sm, int r) {
+template <class SH>
+RD_HD void row_fwd(const SH& S, unsigned char* sm, int r) {
   float4* Z = smemZ(S, sm) + (size_t)(r / S.N1w) * S.pitchZ + (r % S.N1w);
   cf va[16], vb[16];
 #pragma unroll
@@ -137,7 +143,8 @@ RD_HD void row_fwd(const FusedShape& S, unsigned char* sm, int r) {
 
 // Spectrum value of the real plane at (kh, kw >= 0) from the row-transformed band buffer.
 // Returns F[kh, kw] (unnormalised numpy fft2 convention).
-RD_HD cf band_spectrum(const FusedShape& S, const unsigned char* sm, int kh, int kw) {
+template <class SH>
+RD_HD cf band_spectrum(const SH& S, const unsigned char* sm, int kh, int kw) {
   const float4* Z = reinterpret_cast<const float4*>(sm + S.offZ);
   const float* tab = smemTab(S, sm);
   const float* tw2 = tab + S.tTW2 + 2 * kw;  // [c1][kw], row stride 2 * (b + 1)
@@ -168,7 +175,8 @@ RD_HD cf band_spectrum(const FusedShape& S, const unsigned char* sm, int kh, int
 // Band task q = (khi = q / (b+1), kw = q % (b+1)) for the MIX kernel: dF/(HW) into D[khi][kw].
 // `patch` is the partner's [nb][nb] low-band amplitude (fftshift layout, centre = DC);
 // one_minus_ratio = (den - k) / den.
-RD_HD void band_mix(const FusedShape& S, unsigned char* sm, const float* patch, float one_minus_ratio, int q) {
+template <class SH>
+RD_HD void band_mix(const SH& S, unsigned char* sm, const float* patch, float one_minus_ratio, int q) {
   const int kw = q % (S.b + 1), khi = q / (S.b + 1), kh = khi - S.b;
   if (kw == 0 && kh < 0) return;  // written by the (-kh, 0) task
   const cf f = band_spectrum(S, sm, kh, kw);
@@ -192,7 +200,8 @@ RD_HD void band_mix(const FusedShape& S, unsigned char* sm, const float* patch, 
 }
 
 // Band task for the BANK builder: |F| into the global patch at (kh, kw) and (-kh, -kw).
-RD_HD void band_amp(const FusedShape& S, const unsigned char* sm, float* patch, int q) {
+template <class SH>
+RD_HD void band_amp(const SH& S, const unsigned char* sm, float* patch, int q) {
   const int kw = q % (S.b + 1), khi = q / (S.b + 1), kh = khi - S.b;
   if (kw == 0 && kh < 0) return;
   const cf f = band_spectrum(S, sm, kh, kw);
@@ -203,8 +212,8 @@ RD_HD void band_amp(const FusedShape& S, const unsigned char* sm, float* patch, 
 
 // Row inverse: task r = (khi, c1): B[k2] = sum_{kw = k2 mod 16} D[kh][kw] * P{a,b}[c1][kw], radix-16
 // inverse over k2 -> z'[khi][c1 + N1w * j].
-template <int MMAX>
-RD_HD void row_inv(const FusedShape& S, unsigned char* sm, int r) {
+template <int MMAX, class SH>
+RD_HD void row_inv(const SH& S, unsigned char* sm, int r) {
   const int khi = r / S.N1w, c1 = r % S.N1w;
   const float2* D = smemD(S, sm);
   const float2* Dp = D + (size_t)khi * (S.b + 1);
@@ -241,8 +250,8 @@ RD_HD void row_inv(const FusedShape& S, unsigned char* sm, int r) {
 
 // I2: task t = (h1 = t / 16, c = t % 16) of strip `strip`: B[k2] = sum_{kh = k2 mod 16} conj(W_H^(h1 kh)) z'[kh][c4],
 // radix-16 inverse over k2 -> delta at rows h1 + N1h * j; y = clamp(x + delta) * scale + shift.
-template <int MMAX, class LoadF4, class StoreF4>
-RD_HD void col_inv_store(const FusedShape& S, const unsigned char* sm, LoadF4 ld, StoreF4 st, Epilogue ep, int strip, int t) {
+template <int MMAX, class SH, class LoadF4, class StoreF4>
+RD_HD void col_inv_store(const SH& S, const unsigned char* sm, LoadF4 ld, StoreF4 st, Epilogue ep, int strip, int t) {
   const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
   const float4* Z = reinterpret_cast<const float4*>(sm + S.offZ) + c4;
   const float* tw1 = smemTab(S, sm) + S.tTW1 + 2 * (h1 * S.nb + S.b);

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <vector>
 #include "ram_fused_core.cuh"
+#include "ram_fused_static.cuh"
 
 namespace ramdsir {
 
@@ -43,34 +44,25 @@ inline bool fused_shape_init(FusedShape& S, int H, int W, int b) {
   return S.smemBytes <= kFusedMaxSmem;
 }
 
-inline void fused_tables_fill(const FusedShape& S, float* tab) {
-  const double tau = 6.283185307179586476925286766559;
+// PT / TW2 / TW3: the row-pass and band tables shared by the runtime-shape and static-shape kernels
+template <class SH>
+inline void fused_tables_fill_common(const SH& S, float* tab) {
   auto put = [&](int idx, double re, double im) { tab[idx] = (float)re; tab[idx + 1] = (float)im; };
   for (int i = 0; i < S.tabBytes / 4; ++i) tab[i] = 0.f;
-  // exact integer reduction of the phase index keeps the double-precision argument small
-  for (int h1 = 0; h1 < S.N1h; ++h1)
-    for (int khi = 0; khi < S.nb; ++khi) {
-      const long n = (((long)h1 * (khi - S.b)) % S.H + S.H) % S.H;
-      const double a = -tau * (double)n / S.H;
-      put(S.tTW1 + 2 * (h1 * S.nb + khi), std::cos(a), std::sin(a));
-    }
   for (int c1 = 0; c1 < S.N1w; ++c1)
     for (int kw = 0; kw <= S.b; ++kw) {
       const long n = ((long)c1 * kw) % S.M;
-      const double a = -tau * (double)n / S.M;
-      put(S.tTW2 + 2 * (c1 * (S.b + 1) + kw), std::cos(a), std::sin(a));
+      put(S.tTW2 + 2 * (c1 * (S.b + 1) + kw), ct::cos2pi(n, S.M), -ct::sin2pi(n, S.M));
     }
   for (int g = 1; g <= 3; ++g)
     for (int kw = 0; kw <= S.b; ++kw) {
       const long n = ((long)g * kw) % S.W;
-      const double a = -tau * (double)n / S.W;
-      put(S.tTW3 + 2 * ((g - 1) * (S.b + 1) + kw), std::cos(a), std::sin(a));
+      put(S.tTW3 + 2 * ((g - 1) * (S.b + 1) + kw), ct::cos2pi(n, S.W), -ct::sin2pi(n, S.W));
     }
   // PT[c1][kw] = (Qa, Qb)[kw] * W_M^(-c1 kw);  Qa = 1 + i W_W^(-2kw),  Qb = W_W^(-kw) + i W_W^(-3kw)
   auto eW = [&](long n, double& re, double& im) {  // exp(+2 pi i n / W), n reduced exactly
     n = ((n % S.W) + S.W) % S.W;
-    const double a = tau * (double)n / S.W;
-    re = std::cos(a); im = std::sin(a);
+    re = ct::cos2pi(n, S.W); im = ct::sin2pi(n, S.W);
   };
   for (int c1 = 0; c1 < S.N1w; ++c1)
     for (int kwi = 0; kwi < S.nb; ++kwi) {
@@ -83,6 +75,36 @@ inline void fused_tables_fill(const FusedShape& S, float* tab) {
       float* p = tab + S.tPT + 4 * (c1 * S.nb + kwi);
       p[0] = (float)(qar * rm - qai * im); p[1] = (float)(qar * im + qai * rm);
       p[2] = (float)(qbr * rm - qbi * im); p[3] = (float)(qbr * im + qbi * rm);
+    }
+}
+
+inline void fused_tables_fill(const FusedShape& S, float* tab) {
+  fused_tables_fill_common(S, tab);
+  // exact integer reduction of the phase index keeps the double-precision argument small
+  for (int h1 = 0; h1 < S.N1h; ++h1)
+    for (int khi = 0; khi < S.nb; ++khi) {
+      const long n = (((long)h1 * (khi - S.b)) % S.H + S.H) % S.H;
+      tab[S.tTW1 + 2 * (h1 * S.nb + khi)] = (float)ct::cos2pi(n, S.H);
+      tab[S.tTW1 + 2 * (h1 * S.nb + khi) + 1] = (float)-ct::sin2pi(n, S.H);
+    }
+}
+
+// static-shape kernels: common tables + TWH[h1][k2] = W_H^(h1 k2)
+template <class CFG>
+inline void fused_tables_fill_static(float* tab) {
+  CFG S;
+  fused_tables_fill_common(S, tab);
+  for (int h1 = 0; h1 < CFG::N1h; ++h1)
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const long n = ((long)h1 * k2) % CFG::H;
+      tab[CFG::tTWH + 2 * (h1 * CFG::twhPitch + k2)] = (float)ct::cos2pi(n, CFG::H);
+      tab[CFG::tTWH + 2 * (h1 * CFG::twhPitch + k2) + 1] = (float)-ct::sin2pi(n, CFG::H);
+    }
+  for (int c1 = 0; c1 < CFG::N1w; ++c1)
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const long n = ((long)c1 * k2) % CFG::M;
+      tab[CFG::tTWM + 2 * (c1 * 16 + k2)] = (float)ct::cos2pi(n, CFG::M);
+      tab[CFG::tTWM + 2 * (c1 * 16 + k2) + 1] = (float)-ct::sin2pi(n, CFG::M);
     }
 }
 

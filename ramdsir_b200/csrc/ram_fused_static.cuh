@@ -1,0 +1,431 @@
+// Fused RAM pipeline, compile-time shape variant (the BASELINE shapes: 256x256 b=25, 384x384 b=38).
+//
+// Same algorithm and data layout as ram_fused_core.cuh (which stays as the any-shape fallback), with
+// two changes that matter for issue-slot count:
+//   * H, W and the band half-width b are template constants, so every loop bound, band-validity test
+//     and shared-memory offset folds to an immediate;
+//   * the length-N1h stage of the column transforms is a real pruned FFT (radix-4 over h1 = a + Q b'
+//     followed by Q-term twiddled sums with compile-time twiddles) instead of N1h-term direct sums:
+//     ~4x fewer multiply-adds, no twiddle loads, and bit-exact zeros for constant planes, like the
+//     butterflies of the reference's pocketfft.
+// Column index algebra (forward; the inverse conjugates every factor), H = 16 N1h, N1h = 4 Q:
+//   h = h1 + N1h j,  kh = k2 + 16 k1,  h1 = a + Q b'
+//   W_H^(h kh) = W_16^(j k2) * W_H^(h1 k2) * W_N1h^(a k1) * W_4^(b' k1)
+//   fft16 over j (registers) -> twiddle table TWH[h1][k2] -> exchange through E -> fft4 over b' ->
+//   sum over a for the k1 in [-MM, MM-1] whose kh lies in the band.
+#pragma once
+#include "ram_fused_core.cuh"
+
+namespace ramdsir {
+
+constexpr int s_al16(int x) { return (x + 15) & ~15; }
+constexpr int s_max(int a, int b) { return a > b ? a : b; }
+
+template <int H_, int W_, int B_>
+struct SCfg {
+  static constexpr int H = H_, W = W_, b = B_, nb = 2 * B_ + 1;
+  static constexpr int N1h = H_ / 16, M = W_ / 4, N1w = M / 16;
+  static constexpr int Q = N1h / 4;
+  static constexpr int pitchZ = M + 1;             // = 1 (mod 8): row/band tasks map lanes to consecutive kh rows
+  static constexpr int nthreads = 16 * N1h, nstrips = M / 16;
+  static constexpr int MM = B_ / 16 + 1;          // k1 candidates [-MM, MM-1] cover [-16 MM, 16 MM - 1] >= band
+  static constexpr int MMcore = (B_ + 15) / 16;   // what the shared row_inv<MMAX> expects
+  static constexpr int twhPitch = 18;             // float2 per h1 row of TWH (16 used; 18 avoids a 2-way bank conflict)
+  // shared memory (bytes)
+  static constexpr int offZ = 0;
+  static constexpr int zBytes = s_al16(nb * pitchZ * 16);
+  static constexpr int eBytes = 8 * N1h * 16 * 16;
+  static constexpr int dBytes = nb * (B_ + 1) * 8;
+  static constexpr int pBytes = nb * nb * 4;      // symmetrised partner patch, staged per plane
+  static constexpr int offE = zBytes, offD = zBytes;   // D and P alias E (never live together)
+  static constexpr int offP = offD + s_al16(dBytes);
+  static constexpr int offTab = zBytes + s_al16(s_max(eBytes, s_al16(dBytes) + pBytes));
+  // tables (float offsets inside the table block)
+  static constexpr int tPT = 0;
+  static constexpr int tTW2 = tPT + N1w * nb * 4;
+  static constexpr int tTW3 = tTW2 + N1w * (B_ + 1) * 2;
+  static constexpr int tTWH = ((tTW3 + 3 * (B_ + 1) * 2) + 3) & ~3;   // 16-byte aligned for LDS.128
+  static constexpr int tTWM = tTWH + N1h * twhPitch * 2;              // [N1w][16] float2: W_M^(c1 k2)
+  static constexpr int tabBytes = s_al16((tTWM + N1w * 16 * 2) * 4);
+  static constexpr int smemBytes = offTab + tabBytes;
+  static constexpr float invHW = (float)(1.0 / ((double)H_ * (double)W_));
+  static_assert(H_ % 64 == 0 && W_ % 64 == 0, "static fused path needs H, W multiples of 64");
+  static_assert(2 * B_ + 1 <= M && 2 * B_ + 1 <= H_, "band must fit the packed spectrum");
+  static_assert(nthreads >= 256 && nthreads <= 512, "block size out of range");
+};
+
+// ---- F1a: load 16 strided rows, radix-16 over j, multiply by TWH[h1][k2] = W_H^(h1 k2) --------------
+template <class CFG, class LoadF4>
+RD_HD void s_f1_load_fft_tw(LoadF4 ld, const unsigned char* sm, int strip, int t, cf (&va)[16], cf (&vb)[16]) {
+  const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float4 p = ld((size_t)(h1 + CFG::N1h * j) * CFG::M + c4);
+    va[j] = cf{p.x, p.z};
+    vb[j] = cf{p.y, p.w};
+  }
+  fft16<-1>(va);
+  fft16<-1>(vb);
+  const float4* tw = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWH) +
+                     h1 * (CFG::twhPitch / 2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 w = tw[i];
+    if (i > 0) {
+      va[pos16(2 * i)] = cmul(va[pos16(2 * i)], cf{w.x, w.y});
+      vb[pos16(2 * i)] = cmul(vb[pos16(2 * i)], cf{w.x, w.y});
+    }
+    va[pos16(2 * i + 1)] = cmul(va[pos16(2 * i + 1)], cf{w.z, w.w});
+    vb[pos16(2 * i + 1)] = cmul(vb[pos16(2 * i + 1)], cf{w.z, w.w});
+  }
+}
+
+// ---- F1b: publish k2 in [8 half, 8 half + 8) to E[k2l][h1][c] ---------------------------------------
+template <class CFG>
+RD_HD void s_f1_store_half(unsigned char* sm, int t, int half, const cf (&va)[16], const cf (&vb)[16]) {
+  float4* E = reinterpret_cast<float4*>(sm + CFG::offE) + (t >> 4) * 16 + (t & 15);
+#pragma unroll
+  for (int k2l = 0; k2l < 8; ++k2l) {
+    const cf a = half ? va[pos16(8 + k2l)] : va[pos16(k2l)];
+    const cf bq = half ? vb[pos16(8 + k2l)] : vb[pos16(k2l)];
+    E[k2l * CFG::N1h * 16] = make_float4(a.re, a.im, bq.re, bq.im);
+  }
+}
+
+// second stage of the pruned N1h-point transform: out = sum_a W_N1h^(DIR a k1) y[a]
+template <class CFG, int K1, int DIR, int A>
+struct SumA {
+  static RD_HD cf run(const cf (&y)[CFG::Q][4]) {
+    constexpr int r = ((K1 % 4) + 4) % 4;
+    return SumA<CFG, K1, DIR, A - 1>::run(y) + twidN<CFG::N1h, A * K1, DIR>(y[A][r]);
+  }
+};
+template <class CFG, int K1, int DIR>
+struct SumA<CFG, K1, DIR, 0> {
+  static RD_HD cf run(const cf (&y)[CFG::Q][4]) { return y[0][((K1 % 4) + 4) % 4]; }
+};
+
+template <class CFG, int K1>
+struct F1Out {   // emits band rows kh = k2 + 16 k1 for k1 = K1 .. MM-1
+  static RD_HD void run(const cf (&y)[CFG::Q][4], float2* zcol, int k2) {
+    const int kh = k2 + 16 * K1;
+    if (kh >= -CFG::b && kh <= CFG::b) {
+      const cf o = SumA<CFG, K1, -1, CFG::Q - 1>::run(y);
+      zcol[(size_t)(kh + CFG::b) * CFG::pitchZ * 2] = make_float2(o.re, o.im);
+    }
+    F1Out<CFG, K1 + 1>::run(y, zcol, k2);
+  }
+};
+template <class CFG>
+struct F1Out<CFG, CFG::MM> {
+  static RD_HD void run(const cf (&)[CFG::Q][4], float2*, int) {}
+};
+
+// ---- F1c: task u = (col = u & 1, c = (u >> 1) & 15, k2l = u >> 5): pruned N1h-point DFT over h1 -----
+template <class CFG>
+RD_HD void s_f1_pruned(unsigned char* sm, int strip, int half, int u) {
+  const int col = u & 1, c = (u >> 1) & 15, k2l = u >> 5, k2 = 8 * half + k2l;
+  const float2* e = reinterpret_cast<const float2*>(sm + CFG::offE) + ((size_t)k2l * CFG::N1h * 16 + c) * 2 + col;
+  cf y[CFG::Q][4];
+#pragma unroll
+  for (int a = 0; a < CFG::Q; ++a) {
+#pragma unroll
+    for (int bq = 0; bq < 4; ++bq) {
+      const float2 v = e[(a + CFG::Q * bq) * 32];
+      y[a][bq] = cf{v.x, v.y};
+    }
+    fft4<-1>(y[a][0], y[a][1], y[a][2], y[a][3]);
+  }
+  float2* zcol = reinterpret_cast<float2*>(sm + CFG::offZ) + (strip * 16 + c) * 2 + col;
+  F1Out<CFG, -CFG::MM>::run(y, zcol, k2);
+}
+
+// ---- inverse, first stage: task u = (col, c, k2l), k2 = 2 k2l + par: pruned inverse N1h-point DFT ----
+// E'[k2l][h1][c].col = sum_k1 z'[k2 + 16 k1][c].col W_N1h^(-h1 k1)
+template <class CFG, int K1>
+struct InvGather {   // t[r] += in[k1] * W_N1h^(+a k1), for k1 = K1 .. MM-1
+  template <int A>
+  static RD_HD void run(const cf (&in)[2 * CFG::MM], cf (&t)[4]) {
+    constexpr int r = ((K1 % 4) + 4) % 4;
+    t[r] = t[r] + twidN<CFG::N1h, A * K1, 1>(in[K1 + CFG::MM]);
+    InvGather<CFG, K1 + 1>::template run<A>(in, t);
+  }
+};
+template <class CFG>
+struct InvGather<CFG, CFG::MM> {
+  template <int A>
+  static RD_HD void run(const cf (&)[2 * CFG::MM], cf (&)[4]) {}
+};
+
+template <class CFG, int A>
+struct InvA {   // for a = A .. Q-1
+  static RD_HD void run(const cf (&in)[2 * CFG::MM], float2* e) {
+    cf t[4] = {cf{0.f, 0.f}, cf{0.f, 0.f}, cf{0.f, 0.f}, cf{0.f, 0.f}};
+    InvGather<CFG, -CFG::MM>::template run<A>(in, t);
+    fft4<1>(t[0], t[1], t[2], t[3]);
+#pragma unroll
+    for (int bq = 0; bq < 4; ++bq) e[(A + CFG::Q * bq) * 32] = make_float2(t[bq].re, t[bq].im);
+    InvA<CFG, A + 1>::run(in, e);
+  }
+};
+template <class CFG>
+struct InvA<CFG, CFG::Q> {
+  static RD_HD void run(const cf (&)[2 * CFG::MM], float2*) {}
+};
+
+template <class CFG>
+RD_HD void s_inv_pruned(unsigned char* sm, int strip, int par, int u) {
+  const int col = u & 1, c = (u >> 1) & 15, k2l = u >> 5, k2 = 2 * k2l + par;
+  const float2* zcol = reinterpret_cast<const float2*>(sm + CFG::offZ) + (strip * 16 + c) * 2 + col;
+  cf in[2 * CFG::MM];
+#pragma unroll
+  for (int i = 0; i < 2 * CFG::MM; ++i) {
+    const int kh = k2 + 16 * (i - CFG::MM);
+    cf v{0.f, 0.f};
+    if (kh >= -CFG::b && kh <= CFG::b) {
+      const float2 z = zcol[(size_t)(kh + CFG::b) * CFG::pitchZ * 2];
+      v = cf{z.x, z.y};
+    }
+    in[i] = v;
+  }
+  float2* e = reinterpret_cast<float2*>(sm + CFG::offE) + ((size_t)k2l * CFG::N1h * 16 + c) * 2 + col;
+  InvA<CFG, 0>::run(in, e);
+}
+
+// ---- inverse, second stage part 1: thread (h1, c) takes the 8 k2 of one parity from E', applies
+// conj(TWH[h1][k2]) and a radix-8 inverse; results stay in registers until both parities are done ----
+template <class CFG>
+RD_HD void s_inv_fft8(const unsigned char* sm, int t, int par, cf (&pa)[8], cf (&pb)[8]) {
+  const int h1 = t >> 4;
+  const float4* E = reinterpret_cast<const float4*>(sm + CFG::offE) + h1 * 16 + (t & 15);
+  const float2* tw = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWH) +
+                     h1 * CFG::twhPitch + par;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const float4 v = E[m * CFG::N1h * 16];
+    const float2 w = tw[2 * m];
+    pa[m] = cmulc(cf{v.x, v.y}, cf{w.x, w.y});
+    pb[m] = cmulc(cf{v.z, v.w}, cf{w.x, w.y});
+  }
+  fft8<1>(pa);
+  fft8<1>(pb);
+}
+
+// ---- inverse, second stage part 2: radix-2 combine of the two parities, add x, epilogue, store -----
+template <class CFG, int J>
+struct Combine {
+  template <class LoadF4, class StoreF4>
+  static RD_HD void run(LoadF4 ld, StoreF4 st, Epilogue ep, size_t base, const cf (&eva)[8], const cf (&evb)[8],
+                        const cf (&oda)[8], const cf (&odb)[8]) {
+    const cf wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
+    const cf ea = eva[pos8(J)], eb = evb[pos8(J)];
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const size_t off = base + (size_t)(CFG::N1h * (J + 8 * hi)) * CFG::M;
+      const cf a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
+      const float4 x = ld(off);
+      float4 y;
+      y.x = fmaf(fminf(fmaxf(x.x + a.re, ep.lo), ep.hi), ep.scale, ep.shift);
+      y.y = fmaf(fminf(fmaxf(x.y + bq.re, ep.lo), ep.hi), ep.scale, ep.shift);
+      y.z = fmaf(fminf(fmaxf(x.z + a.im, ep.lo), ep.hi), ep.scale, ep.shift);
+      y.w = fmaf(fminf(fmaxf(x.w + bq.im, ep.lo), ep.hi), ep.scale, ep.shift);
+      st(off, y);
+    }
+    Combine<CFG, J + 1>::run(ld, st, ep, base, eva, evb, oda, odb);
+  }
+};
+template <class CFG>
+struct Combine<CFG, 8> {
+  template <class LoadF4, class StoreF4>
+  static RD_HD void run(LoadF4, StoreF4, Epilogue, size_t, const cf (&)[8], const cf (&)[8], const cf (&)[8], const cf (&)[8]) {}
+};
+
+template <class CFG, class LoadF4, class StoreF4>
+RD_HD void s_inv_combine_store(LoadF4 ld, StoreF4 st, Epilogue ep, int strip, int t, const cf (&eva)[8],
+                               const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
+  const size_t base = (size_t)(t >> 4) * CFG::M + strip * 16 + (t & 15);
+  Combine<CFG, 0>::run(ld, st, ep, base, eva, evb, oda, odb);
+}
+
+// =============================================================================================
+// Row passes and band update, static-shape versions.  Lane mapping: consecutive lanes take consecutive
+// band rows kh (row pitch = 1 float4 mod 8 -> conflict-free LDS.128/STS.128).
+//
+// Row index algebra (M = 16 N1w):  c4 = c1 + N1w j,  kw = k2 + 16 q
+//   W_M^(c4 kw) = W_16^(j k2) * W_M^(c1 k2) * W_N1w^(c1 q)
+// row_fwd does the radix-16 over j and the twiddle TWM[c1][k2]; the band task finishes with ONE
+// output of an N1w-point butterfly (exact +-1, +-i for N1w = 4; radix-2 x radix-3 for N1w = 6).
+
+template <class CFG>
+RD_HD void s_row_fwd(unsigned char* sm, int r) {
+  const int khi = r % CFG::nb, c1 = r / CFG::nb;
+  float4* Z = reinterpret_cast<float4*>(sm + CFG::offZ) + (size_t)khi * CFG::pitchZ + c1;
+  cf va[16], vb[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float4 p = Z[CFG::N1w * j];
+    va[j] = cf{p.x, p.y};
+    vb[j] = cf{p.z, p.w};
+  }
+  fft16<-1>(va);
+  fft16<-1>(vb);
+  const float4* tw = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWM) + c1 * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 w = tw[i];
+    cf a0 = va[pos16(2 * i)], b0 = vb[pos16(2 * i)];
+    if (i > 0) {
+      a0 = cmul(a0, cf{w.x, w.y});
+      b0 = cmul(b0, cf{w.x, w.y});
+    }
+    const cf a1 = cmul(va[pos16(2 * i + 1)], cf{w.z, w.w}), b1 = cmul(vb[pos16(2 * i + 1)], cf{w.z, w.w});
+    Z[CFG::N1w * (2 * i)] = make_float4(a0.re, a0.im, b0.re, b0.im);
+    Z[CFG::N1w * (2 * i + 1)] = make_float4(a1.re, a1.im, b1.re, b1.im);
+  }
+}
+
+// one output X[q] = sum_c a[c] W_N^(DIR c q) of an N-point DFT, butterfly-structured
+template <int N, int DIR>
+struct DftOut;
+template <int DIR>
+struct DftOut<4, DIR> {
+  static RD_HD cf run(const cf (&a)[4], int q) {
+    const cf t02p = a[0] + a[2], t02m = a[0] - a[2], t13p = a[1] + a[3], t13m = a[1] - a[3];
+    const cf jt = (DIR < 0) ? cf{t13m.im, -t13m.re} : cf{-t13m.im, t13m.re};  // (DIR i) * t13m
+    const cf e = (q & 1) ? t02m : t02p, o = (q & 1) ? jt : t13p;
+    return (q & 2) ? e - o : e + o;
+  }
+};
+template <int DIR>
+struct DftOut<6, DIR> {
+  static RD_HD cf run(const cf (&a)[6], int q) {
+    cf e[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) e[c] = (q & 1) ? a[c] - a[c + 3] : a[c] + a[c + 3];   // W_6^(3q) = (-1)^q
+    // remaining: sum_c e[c] W_6^(c q); for odd q the factor W_6^(c q) = W_3^(c q') * (W_6^c)^(odd)...
+    // handle by reducing to a 3-point DFT on twiddled inputs: W_6^(c q) = W_3^(c (q >> 1)) * W_6^(c (q & 1))
+    if (q & 1) {
+      e[1] = twidN<6, 1, DIR>(e[1]);
+      e[2] = twidN<6, 2, DIR>(e[2]);
+    }
+    const int r3 = (q >> 1) % 3;
+    const cf s = e[1] + e[2], d = e[1] - e[2];
+    if (r3 == 0) return e[0] + s;
+    constexpr float kS = 0.86602540378443864676f;  // sin(2 pi / 3)
+    const cf m{e[0].re - 0.5f * s.re, e[0].im - 0.5f * s.im};
+    // W_3^(DIR) = -1/2 + DIR i kS ; r3 = 1: e0 + W e1 + W^2 e2 = m + (DIR i kS) d ; r3 = 2: m - (DIR i kS) d
+    const float sg = ((r3 == 1) == (DIR > 0)) ? kS : -kS;
+    return cf{m.re - sg * d.im, m.im + sg * d.re};
+  }
+};
+
+// F[kh, kw] for kw >= 0 from the row-transformed, twiddled band buffer
+template <class CFG>
+RD_HD cf s_band_spectrum(const unsigned char* sm, int kh, int kw) {
+  const float4* Z = reinterpret_cast<const float4*>(sm + CFG::offZ);
+  const float* tab = reinterpret_cast<const float*>(sm + CFG::offTab);
+  const int k2p = kw & 15, qp = kw >> 4;
+  const int k2m = (16 - k2p) & 15, qm = (((-kw - k2m) / 16) % CFG::N1w + CFG::N1w) % CFG::N1w;
+  const float4* zp = Z + (size_t)(kh + CFG::b) * CFG::pitchZ + CFG::N1w * k2p;
+  const float4* zm = Z + (size_t)(CFG::b - kh) * CFG::pitchZ + CFG::N1w * k2m;
+  cf pa[CFG::N1w], pb[CFG::N1w], ma[CFG::N1w], mb[CFG::N1w];
+#pragma unroll
+  for (int c1 = 0; c1 < CFG::N1w; ++c1) {
+    const float4 p = zp[c1], q = zm[c1];
+    pa[c1] = cf{p.x, p.y};
+    pb[c1] = cf{p.z, p.w};
+    ma[c1] = cf{q.x, q.y};
+    mb[c1] = cf{q.z, q.w};
+  }
+  const cf upa = DftOut<CFG::N1w, -1>::run(pa, qp), upb = DftOut<CFG::N1w, -1>::run(pb, qp);
+  const cf uma = DftOut<CFG::N1w, -1>::run(ma, qm), umb = DftOut<CFG::N1w, -1>::run(mb, qm);
+  const cf g0{0.5f * (upa.re + uma.re), 0.5f * (upa.im - uma.im)};
+  const cf g2{0.5f * (upa.im + uma.im), -0.5f * (upa.re - uma.re)};
+  const cf g1{0.5f * (upb.re + umb.re), 0.5f * (upb.im - umb.im)};
+  const cf g3{0.5f * (upb.im + umb.im), -0.5f * (upb.re - umb.re)};
+  const float* tw3 = tab + CFG::tTW3 + 2 * kw;
+  cf f = g0;
+  cmac(f, g1, ldcf(tw3));
+  cmac(f, g2, ldcf(tw3 + 2 * (CFG::b + 1)));
+  cmac(f, g3, ldcf(tw3 + 4 * (CFG::b + 1)));
+  return f;
+}
+
+// stage the partner's patch, symmetrised over +-k, into shared memory: P[i] = (patch[i] + patch[n-1-i]) / 2
+template <class CFG>
+RD_HD void s_stage_patch(unsigned char* sm, const float* patch, int i) {
+  constexpr int n = CFG::nb * CFG::nb;
+  reinterpret_cast<float*>(sm + CFG::offP)[i] = 0.5f * (patch[i] + patch[n - 1 - i]);
+}
+
+template <class CFG>
+RD_HD void s_band_mix(unsigned char* sm, float one_minus_ratio, int q) {
+  const int khi = q % CFG::nb, kw = q / CFG::nb, kh = khi - CFG::b;
+  if (kw == 0 && kh < 0) return;
+  const cf f = s_band_spectrum<CFG>(sm, kh, kw);
+  const float at = reinterpret_cast<const float*>(sm + CFG::offP)[khi * CFG::nb + kw + CFG::b];
+  const float a2 = f.re * f.re + f.im * f.im;
+  cf d;
+  if (a2 > 0.f) {
+    const float s = one_minus_ratio * (at / sqrtf(a2) - 1.0f) * CFG::invHW;
+    d = cf{f.re * s, f.im * s};
+  } else {
+    d = cf{one_minus_ratio * at * CFG::invHW, 0.f};
+  }
+  float2* D = reinterpret_cast<float2*>(sm + CFG::offD);
+  if (kw == 0) {
+    if (kh == 0) d.im = 0.f;
+    D[(size_t)(CFG::nb - 1 - khi) * (CFG::b + 1)] = make_float2(d.re, -d.im);
+  }
+  D[(size_t)khi * (CFG::b + 1) + kw] = make_float2(d.re, d.im);
+}
+
+template <class CFG>
+RD_HD void s_band_amp(const unsigned char* sm, float* patch, int q) {
+  const int khi = q % CFG::nb, kw = q / CFG::nb, kh = khi - CFG::b;
+  if (kw == 0 && kh < 0) return;
+  const cf f = s_band_spectrum<CFG>(sm, kh, kw);
+  const float a = sqrtf(f.re * f.re + f.im * f.im);
+  patch[(size_t)khi * CFG::nb + (kw + CFG::b)] = a;
+  patch[(size_t)(CFG::nb - 1 - khi) * CFG::nb + (CFG::b - kw)] = a;
+}
+
+// inverse rows (direct band sums into the 16 radix-16 inputs, then radix-16 inverse), lanes <-> kh
+template <class CFG>
+RD_HD void s_row_inv(unsigned char* sm, int r) {
+  const int khi = r % CFG::nb, c1 = r / CFG::nb;
+  const float2* D = reinterpret_cast<const float2*>(sm + CFG::offD);
+  const float2* Dp = D + (size_t)khi * (CFG::b + 1);
+  const float2* Dm = D + (size_t)(CFG::nb - 1 - khi) * (CFG::b + 1);
+  const float4* PT = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tPT) +
+                     (size_t)c1 * CFG::nb + CFG::b;
+  cf va[16], vb[16];
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    cf aa{0, 0}, ab{0, 0};
+#pragma unroll
+    for (int mi = -CFG::MM; mi < CFG::MM; ++mi) {
+      const int kw = k2 + 16 * mi;               // compile-time after unrolling
+      if (kw >= -CFG::b && kw <= CFG::b) {
+        cf d;
+        if (kw >= 0) { const float2 t = Dp[kw]; d = cf{t.x, t.y}; }
+        else { const float2 t = Dm[-kw]; d = cf{t.x, -t.y}; }
+        const float4 p = PT[kw];
+        cmac(aa, d, cf{p.x, p.y});
+        cmac(ab, d, cf{p.z, p.w});
+      }
+    }
+    va[k2] = aa;
+    vb[k2] = ab;
+  }
+  fft16<1>(va);
+  fft16<1>(vb);
+  float4* Z = reinterpret_cast<float4*>(sm + CFG::offZ) + (size_t)khi * CFG::pitchZ + c1;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const cf a = va[pos16(j)], bq = vb[pos16(j)];
+    Z[CFG::N1w * j] = make_float4(a.re, a.im, bq.re, bq.im);
+  }
+}
+
+}  // namespace ramdsir

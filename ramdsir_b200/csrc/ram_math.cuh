@@ -6,8 +6,10 @@
 
 #if defined(__CUDACC__)
 #define RD_HD __host__ __device__ __forceinline__
+#define RD_CX __host__ __device__ constexpr
 #else
 #define RD_HD inline
+#define RD_CX constexpr
 #endif
 
 namespace ramdsir {
@@ -85,6 +87,68 @@ RD_HD void fft16(cf (&v)[16]) {
   v[3 + 4 * 3] = twid16<9, DIR>(v[3 + 4 * 3]);
 #pragma unroll
   for (int k2 = 0; k2 < 4; ++k2) fft4<DIR>(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compile-time twiddles exp(DIR * 2 pi i * M / N) for arbitrary N (used by the pruned N1 stages).
+// Taylor series in double on an argument reduced to |x| <= pi/4: exact to double rounding.
+namespace ct {
+constexpr double kPi = 3.14159265358979323846264338327950288;
+RD_CX double sin_small(double x) {  // |x| <= pi/4
+  double term = x, sum = x;
+  for (int i = 1; i < 14; ++i) {
+    term *= -x * x / ((2 * i) * (2 * i + 1));
+    sum += term;
+  }
+  return sum;
+}
+RD_CX double cos_small(double x) {
+  double term = 1.0, sum = 1.0;
+  for (int i = 1; i < 14; ++i) {
+    term *= -x * x / ((2 * i - 1) * (2 * i));
+    sum += term;
+  }
+  return sum;
+}
+// cos / sin of 2 pi m / n with exact octant reduction on the integers
+RD_CX double cos2pi(long m, long n) {
+  m = ((m % n) + n) % n;
+  if (2 * m > n) m = n - m;                 // cos is even about pi
+  if (4 * m > n) return -cos2pi(n - 2 * m, 2 * n) ;  // cos(x) = -cos(pi - x); pi - x = 2 pi (n - 2m) / (2n)
+  if (8 * m > n) return sin_small(2 * kPi * (double)(n - 4 * m) / (double)(4 * n));  // cos(x) = sin(pi/2 - x)
+  return cos_small(2 * kPi * (double)m / (double)n);
+}
+RD_CX double sin2pi(long m, long n) { return cos2pi(4 * m - n, 4 * n); }  // sin(x) = cos(x - pi/2)
+}  // namespace ct
+
+template <int N, int M, int DIR>
+RD_HD cf twidN(cf a) {
+  constexpr int m = ((M % N) + N) % N;
+  if (m == 0) return a;
+  if (4 * m == N) return (DIR < 0) ? cf{a.im, -a.re} : cf{-a.im, a.re};
+  if (2 * m == N) return cf{-a.re, -a.im};
+  if (4 * m == 3 * N) return (DIR < 0) ? cf{-a.im, a.re} : cf{a.im, -a.re};
+  constexpr float c = (float)ct::cos2pi(m, N);
+  constexpr float s = (float)((DIR < 0) ? -ct::sin2pi(m, N) : ct::sin2pi(m, N));
+  return cf{a.re * c - a.im * s, a.re * s + a.im * c};
+}
+
+// 8-point DFT in place; X[k] ends at v[pos8(k)].
+RD_HD constexpr int pos8(int k) { return (k >> 1) + 4 * (k & 1); }
+
+template <int DIR>
+RD_HD void fft8(cf (&v)[8]) {
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const cf a = v[n] + v[n + 4], d = v[n] - v[n + 4];
+    v[n] = a;
+    v[n + 4] = d;
+  }
+  v[5] = twidN<8, 1, DIR>(v[5]);
+  v[6] = twidN<8, 2, DIR>(v[6]);
+  v[7] = twidN<8, 3, DIR>(v[7]);
+  fft4<DIR>(v[0], v[1], v[2], v[3]);  // X[2k]
+  fft4<DIR>(v[4], v[5], v[6], v[7]);  // X[2k+1]
 }
 
 }  // namespace ramdsir

@@ -171,6 +171,23 @@ def test_white_noise_inputs(R):
     check(got, want, "white noise")
 
 
+@pytest.mark.parametrize("shape", [(3, 256, 256, True), (1, 384, 384, False)])
+def test_constant_planes_take_phase_zero_like_the_reference(R, shape):
+    """A constant plane has EXACT zeros off DC in the reference's butterfly FFT, so those bins take
+    phase 0 (np.angle(0) == 0).  The static fused kernels keep every stage a butterfly and match."""
+    c, h, w, integer = shape
+    rs = np.random.RandomState(17)
+    lo, hi = (0, 255) if integer else (-1, 1)
+    src = _smooth(rs, (3, c, h, w), lo, hi, integer)
+    par = _smooth(rs, (2, c, h, w), lo, hi, integer)
+    src[0, 0] = 77.0 if integer else 0.25          # one constant channel
+    src[1] = 0.0                                    # an all-zero image
+    pidx, rk = np.array([0, 1, 1]), np.array([3, 7, 5], np.int32)
+    epi = O.FUNDUS_EPILOGUE if integer else O.PROSTATE_EPILOGUE
+    got, _ = gpu_mix(R, src, par, pidx, rk, 0.1, epi)
+    check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "constant planes")
+
+
 def test_generic_and_fused_paths_agree(R):
     rs = np.random.RandomState(9)
     src = _smooth(rs, (6, 3, 256, 256), 0, 255, True)

@@ -74,6 +74,81 @@ extern "C" int emul_fused(const float* src, const float* bank, const long long* 
   return 2;
 }
 
+// ---- static-shape (v2) pipeline ------------------------------------------------------------
+template <class CFG>
+static void run_plane_static(unsigned char* sm, const float* x, const float* patch, float omr, float* y,
+                             Epilogue ep, float* bank_out) {
+  CFG S;
+  auto ld = [&](size_t off) { const float* p = x + 4 * off; return make_float4(p[0], p[1], p[2], p[3]); };
+  auto st = [&](size_t off, float4 v) { float* p = y + 4 * off; p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; };
+  constexpr int NT = CFG::nthreads;
+  std::vector<cf> regs((size_t)NT * 32);
+  auto A = [&](int t) -> cf(&)[16] { return *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]); };
+  auto Bv = [&](int t) -> cf(&)[16] { return *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32 + 16]); };
+  for (int strip = 0; strip < CFG::nstrips; ++strip) {
+    for (int t = 0; t < NT; ++t) s_f1_load_fft_tw<CFG>(ld, sm, strip, t, A(t), Bv(t));
+    for (int half = 0; half < 2; ++half) {
+      for (int t = 0; t < NT; ++t) s_f1_store_half<CFG>(sm, t, half, A(t), Bv(t));
+      for (int u = 0; u < 256; ++u) s_f1_pruned<CFG>(sm, strip, half, u);
+    }
+  }
+  for (int r = 0; r < CFG::nb * CFG::N1w; ++r) s_row_fwd<CFG>(sm, r);
+  if (bank_out) {
+    for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) s_band_amp<CFG>(sm, bank_out, q);
+    return;
+  }
+  for (int i = 0; i < CFG::nb * CFG::nb; ++i) s_stage_patch<CFG>(sm, patch, i);
+  for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) s_band_mix<CFG>(sm, omr, q);
+  for (int r = 0; r < CFG::nb * CFG::N1w; ++r) s_row_inv<CFG>(sm, r);
+  (void)S;
+  for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
+    for (int par = 0; par < 2; ++par) {
+      for (int u = 0; u < 256; ++u) s_inv_pruned<CFG>(sm, strip, par, u);
+      for (int t = 0; t < NT; ++t) {
+        cf(&pa)[8] = *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 32 + 16 * par]);
+        cf(&pb)[8] = *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 32 + 16 * par + 8]);
+        s_inv_fft8<CFG>(sm, t, par, pa, pb);
+      }
+    }
+    for (int t = 0; t < NT; ++t) {
+      cf* r = &regs[(size_t)t * 32];
+      s_inv_combine_store<CFG>(ld, st, ep, strip, t, *reinterpret_cast<cf(*)[8]>(r), *reinterpret_cast<cf(*)[8]>(r + 8),
+                               *reinterpret_cast<cf(*)[8]>(r + 16), *reinterpret_cast<cf(*)[8]>(r + 24));
+    }
+  }
+}
+
+template <class CFG>
+static int run_all_static(const float* src, const float* bank, const long long* pidx, const int* rk, int den,
+                          float* out, int B, int C, Epilogue ep, float* bank_out) {
+  std::vector<unsigned char> sm(CFG::smemBytes);
+  fused_tables_fill_static<CFG>(reinterpret_cast<float*>(sm.data() + CFG::offTab));
+  const size_t plane = (size_t)CFG::H * CFG::W, psz = (size_t)CFG::nb * CFG::nb;
+  for (int i = 0; i < B; ++i)
+    for (int c = 0; c < C; ++c) {
+      const size_t p = (size_t)i * C + c;
+      if (bank_out) { run_plane_static<CFG>(sm.data(), src + p * plane, nullptr, 0.f, nullptr, ep, bank_out + p * psz); continue; }
+      const float omr = (float)(den - rk[i]) / (float)den;
+      run_plane_static<CFG>(sm.data(), src + p * plane, bank + ((size_t)pidx[i] * C + c) * psz, omr, out + p * plane, ep, nullptr);
+    }
+  return 0;
+}
+
+extern "C" int emul_fused_static(const float* src, const float* bank, const long long* pidx, const int* rk, int den,
+                                 float* out, int B, int C, int H, int W, int b, float lo, float hi, float scale,
+                                 float shift, float* bank_out) {
+  Epilogue ep{lo, hi, scale, shift};
+  if (H == 256 && W == 256 && b == 25) return run_all_static<SCfg<256, 256, 25>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+  if (H == 384 && W == 384 && b == 38) return run_all_static<SCfg<384, 384, 38>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+  return 1;
+}
+
+extern "C" int emul_fused_static_smem_bytes(int H, int W, int b) {
+  if (H == 256 && W == 256 && b == 25) return SCfg<256, 256, 25>::smemBytes;
+  if (H == 384 && W == 384 && b == 38) return SCfg<384, 384, 38>::smemBytes;
+  return -1;
+}
+
 extern "C" int emul_fused_smem_bytes(int H, int W, int b) {
   FusedShape S;
   return fused_shape_init(S, H, W, b) ? S.smemBytes : -1;
