@@ -68,6 +68,10 @@ int ramdsir_path(int C, int H, int W, int b);
  * independent CUDA implementations can be compared; 0 restores automatic selection. */
 int ramdsir_force_path(int path);
 
+/* Tuning/testing knob for the fused path: 0 = auto (float4 static-shape kernels where instantiated),
+ * 1 = "P2" static kernels (one packed column per thread, 64 registers), 2 = runtime-shape kernel. */
+int ramdsir_set_fused_variant(int variant);
+
 /* Scratch bytes needed to process `n_images` images of this shape in one call (0 for the fused path). */
 size_t ramdsir_workspace_bytes(int n_images, int C, int H, int W, int b);
 

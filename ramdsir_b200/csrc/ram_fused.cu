@@ -1,6 +1,7 @@
 // Fused RAM kernels for sm_100a: one persistent CTA per image plane, band buffers in shared memory.
 // See ram_fused_core.cuh for the algorithm and the reference lines it follows
 // (/root/reference/code/dataset/fundus.py:13-61).
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -190,28 +191,142 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// P2 kernel (ram_fused_p2.cuh): one packed complex column per thread, 64 registers, 1024 threads/SM.
+__device__ __forceinline__ float2 ldg_policy2(const float2* p, unsigned long long pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_policy2(float2* p, float2 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+// a warp (one h1, 32 columns) loads 16 rows x 256 bytes per strip = 32 lines: one prefetch per lane
+template <class CFG>
+__device__ __forceinline__ void prefetch_strip_p2(const float2* x2, int strip, int tid) {
+  const int lane = tid & 31, h1 = tid >> 5;
+  prefetch_l2(x2 + (size_t)(h1 + CFG::N1h * (lane >> 1)) * CFG::M2 + strip * 32 + (lane & 1) * 16);
+}
+
+template <class CFG, bool BANK>
+__global__ void __launch_bounds__(CFG::nthreads, (CFG::smemBytes <= 113 * 1024) ? 2 : 1)
+ram_fused_p2_kernel(const float* __restrict__ src, const float* __restrict__ bank, const int64_t* __restrict__ pidx,
+                    const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ out,
+                    const Epilogue ep, const float* __restrict__ tables, int nplanes) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  constexpr int NT = CFG::nthreads;
+  const int tid = threadIdx.x;
+  unsigned long long pol_keep, pol_stream;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  {
+    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
+    const float4* g = reinterpret_cast<const float4*>(tables);
+    for (int i = tid; i < CFG::tabBytes / 16; i += NT) tab[i] = g[i];
+  }
+  __syncthreads();
+  constexpr size_t plane_px = (size_t)CFG::H * CFG::W;
+  constexpr size_t patch_px = (size_t)CFG::nb * CFG::nb;
+  const bool worker = tid < CFG::npruned;          // pruned-stage tasks: 2 parities x 256
+  const int par2 = tid >> 8, u = tid & 255;
+  for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
+    const float2* x2 = reinterpret_cast<const float2*>(src + plane * plane_px);
+    auto ld_first = [&](size_t off) { return BANK ? __ldg(x2 + off) : ldg_policy2(x2 + off, pol_keep); };
+    for (int strip = 0; strip < CFG::nstrips; ++strip) {
+      cf v[16];
+      p_f1_load_fft_tw<CFG>(ld_first, sm, strip, tid, v);
+      if (strip + 1 < CFG::nstrips) prefetch_strip_p2<CFG>(x2, strip + 1, tid);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        p_f1_store_half<CFG>(sm, tid, half, v);
+        __syncthreads();
+        if (worker) {
+          if (par2 == 0) p_f1_pruned<CFG, 0>(sm, strip, half, u);
+          else p_f1_pruned<CFG, 1>(sm, strip, half, u);
+        }
+        __syncthreads();
+      }
+    }
+    Epilogue epp = ep;
+    float omr = 0.f;
+    if (!BANK) {
+      const int img = plane / C, ch = plane - img * C;
+      const long long p = pidx[img];
+      const bool ok = (p >= 0 && p < (long long)n_bank);
+      if (!ok) epp.scale = __int_as_float(0x7fc00000);
+      omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
+      const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
+      for (int i = tid; i < (int)patch_px; i += NT) s_stage_patch<CFG>(sm, patch, i);
+    }
+    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) p_row_fwd<CFG>(sm, r);
+    __syncthreads();
+    if (BANK) {
+      float* patch = out + plane * patch_px;
+      for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) p_band_amp<CFG>(sm, patch, q);
+      __syncthreads();
+      continue;
+    }
+    for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) p_band_mix<CFG>(sm, omr, q);
+    __syncthreads();
+    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) p_row_inv<CFG>(sm, r);
+    __syncthreads();
+    {
+      float2* y2 = reinterpret_cast<float2*>(out + plane * plane_px);
+      auto ld_again = [&](size_t off) { return ldg_policy2(x2 + off, pol_stream); };
+      auto st = [&](size_t off, float2 v) { stg_policy2(y2 + off, v, pol_stream); };
+      const int next = plane + gridDim.x;
+      for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
+        cf ev[8], od[8];
+        if (strip > 0) prefetch_strip_p2<CFG>(x2, strip - 1, tid);
+        else if (next < nplanes) prefetch_strip_p2<CFG>(reinterpret_cast<const float2*>(src + next * plane_px), 0, tid);
+        if (worker) {
+          if (par2 == 0) p_inv_pruned<CFG, 0>(sm, strip, 0, u);
+          else p_inv_pruned<CFG, 1>(sm, strip, 0, u);
+        }
+        __syncthreads();
+        p_inv_fft8<CFG>(sm, tid, 0, ev);
+        __syncthreads();
+        if (worker) {
+          if (par2 == 0) p_inv_pruned<CFG, 0>(sm, strip, 1, u);
+          else p_inv_pruned<CFG, 1>(sm, strip, 1, u);
+        }
+        __syncthreads();
+        p_inv_fft8<CFG>(sm, tid, 1, od);
+        __syncthreads();
+        p_inv_combine_store<CFG>(ld_again, st, epp, strip, tid, ev, od);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 namespace {
 struct FusedPlan {
   FusedShape S;
   float* tables = nullptr;  // device
   int sm_count = 0;
-  int static_id = 0;        // 0: runtime-shape kernel; 1: SCfg<256,256,25>; 2: SCfg<384,384,38>
+  int static_id = 0;        // 0: runtime-shape kernel; 1/2: SCfg<256..>/<384..> (float4); 3/4: PCfg (float2, default)
 };
 using Cfg256 = SCfg<256, 256, 25>;
 using Cfg384 = SCfg<384, 384, 38>;
-int static_id_of(int H, int W, int b) {
-  if (H == 256 && W == 256 && b == 25) return 1;
-  if (H == 384 && W == 384 && b == 38) return 2;
+using P256 = PCfg<256, 256, 25>;
+using P384 = PCfg<384, 384, 38>;
+std::atomic<int> g_variant{0};   // RAMDSIR_VARIANT_*: 0 auto (= float4 static kernels), 1 P2, 2 runtime-shape
+int static_id_of(int H, int W, int b, int variant) {
+  if (variant == 2) return 0;
+  const int base = (variant == 1) ? 2 : 0;
+  if (H == 256 && W == 256 && b == 25) return base + 1;
+  if (H == 384 && W == 384 && b == 38) return base + 2;
   return 0;
 }
 std::mutex g_mu;
-std::map<std::tuple<int, int, int, int>, FusedPlan> g_plans;  // (device, H, W, b)
+std::map<std::tuple<int, int, int, int, int>, FusedPlan> g_plans;  // (device, H, W, b, variant)
 
 int get_plan(int H, int W, int b, FusedPlan** out) {
   int dev = 0;
   RD_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_mu);
-  auto key = std::make_tuple(dev, H, W, b);
+  const int variant = g_variant.load(std::memory_order_relaxed);
+  auto key = std::make_tuple(dev, H, W, b, variant);
   auto it = g_plans.find(key);
   if (it == g_plans.end()) {
     FusedPlan p;
@@ -219,11 +334,14 @@ int get_plan(int H, int W, int b, FusedPlan** out) {
       set_error("fused path does not support H=%d W=%d b=%d", H, W, b);
       return RAMDSIR_ERR_UNSUPPORTED;
     }
-    p.static_id = static_id_of(H, W, b);
-    const int tab_bytes = p.static_id == 1 ? Cfg256::tabBytes : p.static_id == 2 ? Cfg384::tabBytes : p.S.tabBytes;
+    p.static_id = static_id_of(H, W, b, variant);
+    const int tab_bytes = p.static_id == 1 ? Cfg256::tabBytes : p.static_id == 2 ? Cfg384::tabBytes
+                        : p.static_id == 3 ? P256::tabBytes : p.static_id == 4 ? P384::tabBytes : p.S.tabBytes;
     std::vector<float> host(tab_bytes / 4);
     if (p.static_id == 1) fused_tables_fill_static<Cfg256>(host.data());
     else if (p.static_id == 2) fused_tables_fill_static<Cfg384>(host.data());
+    else if (p.static_id == 3) fused_tables_fill_p2<P256>(host.data());
+    else if (p.static_id == 4) fused_tables_fill_p2<P384>(host.data());
     else fused_tables_fill(p.S, host.data());
     RD_CUDA(cudaMalloc(&p.tables, tab_bytes));
     RD_CUDA(cudaMemcpy(p.tables, host.data(), tab_bytes, cudaMemcpyHostToDevice));
@@ -256,9 +374,18 @@ int launch(const FusedPlan& p, const float* src, const float* bank, const int64_
 }
 
 template <class CFG, bool BANK>
+struct KernelOf {
+  static auto get() { return ram_fused_static_kernel<CFG, BANK>; }
+};
+template <int H, int W, int B, bool BANK>
+struct KernelOf<PCfg<H, W, B>, BANK> {
+  static auto get() { return ram_fused_p2_kernel<PCfg<H, W, B>, BANK>; }
+};
+
+template <class CFG, bool BANK>
 int launch_static(const FusedPlan& p, const float* src, const float* bank, const int64_t* pidx, const int32_t* rk,
                   int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
-  auto kern = ram_fused_static_kernel<CFG, BANK>;
+  auto kern = KernelOf<CFG, BANK>::get();
   static thread_local int per_sm = 0;  // per instantiation
   if (per_sm == 0) {
     RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
@@ -278,6 +405,8 @@ int dispatch(const FusedPlan& p, const float* src, const float* bank, const int6
              int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
   if (p.static_id == 1) return launch_static<Cfg256, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
   if (p.static_id == 2) return launch_static<Cfg384, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
+  if (p.static_id == 3) return launch_static<P256, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
+  if (p.static_id == 4) return launch_static<P384, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
   switch (p.S.MM) {
     case 0:
     case 1: return launch<1, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
@@ -289,6 +418,8 @@ int dispatch(const FusedPlan& p, const float* src, const float* bank, const int6
   return RAMDSIR_ERR_UNSUPPORTED;
 }
 }  // namespace
+
+void fused_set_variant(int v) { g_variant.store(v, std::memory_order_relaxed); }
 
 bool fused_supported(int H, int W, int b) {
   FusedShape S;

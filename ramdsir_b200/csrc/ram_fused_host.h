@@ -5,6 +5,7 @@
 #include <vector>
 #include "ram_fused_core.cuh"
 #include "ram_fused_static.cuh"
+#include "ram_fused_p2.cuh"
 
 namespace ramdsir {
 
@@ -105,6 +106,32 @@ inline void fused_tables_fill_static(float* tab) {
       const long n = ((long)c1 * k2) % CFG::M;
       tab[CFG::tTWM + 2 * (c1 * 16 + k2)] = (float)ct::cos2pi(n, CFG::M);
       tab[CFG::tTWM + 2 * (c1 * 16 + k2) + 1] = (float)-ct::sin2pi(n, CFG::M);
+    }
+}
+
+// P2 kernels (one packed complex column per thread): PT, TW3, TWH, TWM
+template <class CFG>
+inline void fused_tables_fill_p2(float* tab) {
+  for (int i = 0; i < CFG::tabBytes / 4; ++i) tab[i] = 0.f;
+  auto put = [&](int idx, double re, double im) { tab[idx] = (float)re; tab[idx + 1] = (float)im; };
+  for (int c1 = 0; c1 < CFG::N1w; ++c1)
+    for (int kwi = 0; kwi < CFG::nb; ++kwi) {
+      const long kw = kwi - CFG::b;
+      const double r1 = ct::cos2pi(kw, CFG::W), i1 = ct::sin2pi(kw, CFG::W);          // W_W^-kw
+      const double rm = ct::cos2pi(2L * c1 * kw, CFG::W), im = ct::sin2pi(2L * c1 * kw, CFG::W);  // W_M2^(-c1 kw)
+      const double qr = 1.0 - i1, qi = r1;                                             // 1 + i W_W^-kw
+      put(CFG::tPT + 2 * (c1 * CFG::nb + kwi), qr * rm - qi * im, qr * im + qi * rm);
+    }
+  for (int kw = 0; kw <= CFG::b; ++kw) put(CFG::tTW3 + 2 * kw, ct::cos2pi(kw, CFG::W), -ct::sin2pi(kw, CFG::W));
+  for (int h1 = 0; h1 < CFG::N1h; ++h1)
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const long n = ((long)h1 * k2) % CFG::H;
+      put(CFG::tTWH + 2 * (h1 * CFG::twhPitch + k2), ct::cos2pi(n, CFG::H), -ct::sin2pi(n, CFG::H));
+    }
+  for (int c1 = 0; c1 < CFG::N1w; ++c1)
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const long n = ((long)c1 * k2) % CFG::M2;
+      put(CFG::tTWM + 2 * (c1 * 16 + k2), ct::cos2pi(n, CFG::M2), -ct::sin2pi(n, CFG::M2));
     }
 }
 

@@ -31,8 +31,15 @@ struct MixArgs {
 
 // fused single-CTA-per-plane path (ram_fused.cu)
 bool fused_supported(int H, int W, int b);
+void fused_set_variant(int v);
 int fused_mix(const MixArgs& a, cudaStream_t st);
 int fused_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st);
+
+// multi-pass path for large planes (ram_multipass.cu)
+bool multipass_supported(int H, int W, int b);
+size_t multipass_workspace_bytes(int n_images, int C, int H, int W, int b);
+int multipass_mix(const MixArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
+int multipass_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // any-shape direct band-pruned DFT path (ram_generic.cu)
 bool generic_supported(int H, int W, int b);

@@ -1,0 +1,253 @@
+// Multi-pass RAM kernels (K2) for sm_100a: 512^2 (b = 51) and 1024^2 (b = 102).  See ram_multipass.cuh.
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+#include "ram_internal.h"
+#include "ram_multipass_host.h"
+
+namespace ramdsir {
+
+__device__ __forceinline__ float4 mp_ldg_policy(const float4* p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void mp_stg_policy(float4* p, float4 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
+// ---- pass A: forward columns of one (plane, strip) -> Zg[plane][kh][strip columns] --------------------
+template <class CFG>
+__global__ void __launch_bounds__(256, 2)
+ram_mp_pass_a(const float* __restrict__ src, float4* __restrict__ Zg, const float* __restrict__ tables, int plane0) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, lp = blockIdx.x / CFG::nstrips;
+  unsigned long long pol_keep;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  {
+    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
+    const float4* g = reinterpret_cast<const float4*>(tables);
+    for (int i = tid; i < CFG::tabBytes / 16; i += 256) tab[i] = g[i];
+  }
+  __syncthreads();
+  const float4* x4 = reinterpret_cast<const float4*>(src + (size_t)(plane0 + lp) * CFG::H * CFG::W);
+  auto ld = [&](size_t off) { return mp_ldg_policy(x4 + off, pol_keep); };
+  for (int p = 0; p < CFG::HP; ++p) {
+    cf va[16], vb[16];
+    m_f1_load_fft_tw<CFG>(ld, sm, strip, p, tid, va, vb);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      s_f1_store_half<CFG>(sm, tid, half, va, vb);
+      __syncthreads();
+      m_f1_pruned<CFG>(sm, p, half, tid);
+      __syncthreads();
+    }
+  }
+  const float4* Zs = reinterpret_cast<const float4*>(sm + CFG::offZ);
+  float4* zg = Zg + (size_t)lp * CFG::nb * CFG::M + strip * 16;
+  for (int i = tid; i < CFG::nb * 16; i += 256) zg[(size_t)(i >> 4) * CFG::M + (i & 15)] = Zs[(i >> 4) * CFG::pitchZ + (i & 15)];
+}
+
+// ---- pass B: rows +kh and -kh of one plane: row FFTs, band update, inverse row FFTs, in place ---------
+template <class CFG, bool BANK>
+__global__ void __launch_bounds__(CFG::bThreads)
+ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank, const int64_t* __restrict__ pidx,
+              const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ bank_out,
+              const float* __restrict__ tables, int plane0) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  constexpr int NT = CFG::bThreads;
+  const int tid = threadIdx.x, kh = blockIdx.x % (CFG::b + 1), lp = blockIdx.x / (CFG::b + 1);
+  const int plane = plane0 + lp, nrows = (kh == 0) ? 1 : 2;
+  {
+    float4* tab = reinterpret_cast<float4*>(sm + CFG::bOffTab);
+    const float4* g = reinterpret_cast<const float4*>(tables);
+    for (int i = tid; i < CFG::bTabBytes / 16; i += NT) tab[i] = g[i];
+  }
+  float4* R = reinterpret_cast<float4*>(sm + CFG::bOffR);
+  float4* zrow[2] = {Zg + ((size_t)lp * CFG::nb + (CFG::b + kh)) * CFG::M, Zg + ((size_t)lp * CFG::nb + (CFG::b - kh)) * CFG::M};
+  for (int i = tid; i < nrows * CFG::M; i += NT) R[(i / CFG::M) * CFG::rowPitch + (i % CFG::M)] = zrow[i / CFG::M][i % CFG::M];
+  __syncthreads();
+  for (int t = tid; t < nrows * CFG::N1w; t += NT) m_row_stage1<CFG, -1>(sm, t);
+  __syncthreads();
+  for (int t = tid; t < nrows * 16; t += NT) m_row_stage2<CFG, -1>(sm, t);
+  __syncthreads();
+  const size_t patch_px = (size_t)CFG::nb * CFG::nb;
+  if (BANK) {
+    float* patch = bank_out + (size_t)plane * patch_px;
+    for (int t = tid; t < nrows * (CFG::b + 1); t += NT) m_band<CFG, true>(sm, nullptr, patch, 0.f, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+    return;
+  }
+  {
+    const int img = plane / C, ch = plane - img * C;
+    const long long p = pidx[img];
+    const bool ok = (p >= 0 && p < (long long)n_bank);
+    const float omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
+    const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
+    for (int t = tid; t < nrows * (CFG::b + 1); t += NT) m_band<CFG, false>(sm, patch, nullptr, omr, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+  }
+  __syncthreads();
+  for (int t = tid; t < nrows * CFG::M; t += NT) m_fill_v<CFG>(sm, kh, t / CFG::M, t % CFG::M);
+  __syncthreads();
+  for (int t = tid; t < nrows * 16; t += NT) m_row_stage2<CFG, 1>(sm, t);
+  __syncthreads();
+  for (int t = tid; t < nrows * CFG::N1w; t += NT) m_row_stage1<CFG, 1>(sm, t);
+  __syncthreads();
+  for (int i = tid; i < nrows * CFG::M; i += NT) zrow[i / CFG::M][i % CFG::M] = R[(i / CFG::M) * CFG::rowPitch + (i % CFG::M)];
+}
+
+// ---- pass C: inverse columns of one (plane, strip), + x, epilogue -------------------------------------
+template <class CFG>
+__global__ void __launch_bounds__(256, 2)
+ram_mp_pass_c(const float* __restrict__ src, const float4* __restrict__ Zg, const int64_t* __restrict__ pidx, int n_bank,
+              int C, float* __restrict__ out, Epilogue ep, const float* __restrict__ tables, int plane0) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, lp = blockIdx.x / CFG::nstrips;
+  const int plane = plane0 + lp;
+  unsigned long long pol_stream;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  {
+    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
+    const float4* g = reinterpret_cast<const float4*>(tables);
+    for (int i = tid; i < CFG::tabBytes / 16; i += 256) tab[i] = g[i];
+    float4* Zs = reinterpret_cast<float4*>(sm + CFG::offZ);
+    const float4* zg = Zg + (size_t)lp * CFG::nb * CFG::M + strip * 16;
+    for (int i = tid; i < CFG::nb * 16; i += 256) Zs[(i >> 4) * CFG::pitchZ + (i & 15)] = zg[(size_t)(i >> 4) * CFG::M + (i & 15)];
+  }
+  {
+    const long long p = pidx[plane / C];
+    if (p < 0 || p >= (long long)n_bank) ep.scale = __int_as_float(0x7fc00000);
+  }
+  __syncthreads();
+  const size_t plane_px = (size_t)CFG::H * CFG::W;
+  const float4* x4 = reinterpret_cast<const float4*>(src + plane * plane_px);
+  float4* y4 = reinterpret_cast<float4*>(out + plane * plane_px);
+  auto ld = [&](size_t off) { return mp_ldg_policy(x4 + off, pol_stream); };
+  auto st = [&](size_t off, float4 v) { mp_stg_policy(y4 + off, v, pol_stream); };
+  const int h1 = tid >> 4, c4 = strip * 16 + (tid & 15);
+  for (int p = 0; p < CFG::HP; ++p) {
+    cf eva[8], evb[8], oda[8], odb[8];
+    m_inv_pruned<CFG>(sm, p, 0, tid);
+    __syncthreads();
+    s_inv_fft8<CFG>(sm, tid, 0, eva, evb);
+    __syncthreads();
+    m_inv_pruned<CFG>(sm, p, 1, tid);
+    __syncthreads();
+    s_inv_fft8<CFG>(sm, tid, 1, oda, odb);
+    __syncthreads();
+    MCombine<CFG, 0>::run(ld, st, ep, h1, p, c4, eva, evb, oda, odb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+using K512 = KCfg<512, 512, 51>;
+using K1024 = KCfg<1024, 1024, 102>;
+
+struct MpPlan {
+  float* tab_ac = nullptr;
+  float* tab_b = nullptr;
+  int chunk = 1;
+};
+std::mutex g_mu;
+std::map<std::tuple<int, int>, MpPlan> g_plans;  // (device, H)
+
+template <class CFG>
+int get_plan(MpPlan** out) {
+  int dev = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_tuple(dev, CFG::H);
+  auto it = g_plans.find(key);
+  if (it == g_plans.end()) {
+    MpPlan p;
+    std::vector<float> a(CFG::tabBytes / 4), b(CFG::bTabBytes / 4);
+    multipass_tables_ac<CFG>(a.data());
+    multipass_tables_b<CFG>(b.data());
+    RD_CUDA(cudaMalloc(&p.tab_ac, CFG::tabBytes));
+    RD_CUDA(cudaMalloc(&p.tab_b, CFG::bTabBytes));
+    RD_CUDA(cudaMemcpy(p.tab_ac, a.data(), CFG::tabBytes, cudaMemcpyHostToDevice));
+    RD_CUDA(cudaMemcpy(p.tab_b, b.data(), CFG::bTabBytes, cudaMemcpyHostToDevice));
+    RD_CUDA(cudaDeviceSynchronize());
+    RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_a<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
+    RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_c<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
+    RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_b<CFG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::bSmemBytes));
+    RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_b<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::bSmemBytes));
+    // chunk of planes per pass: keep x (H*W*4 per plane) + Zg of a chunk well inside the 126 MB L2,
+    // and make planes*strips a multiple of the 296 resident CTAs where possible
+    int sms = 148;
+    RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t per_plane = (size_t)CFG::H * CFG::W * 4 + (size_t)CFG::nb * CFG::M * 16;
+    int chunk = (int)((size_t)90 * 1024 * 1024 / per_plane);
+    const int wave = 2 * sms / CFG::nstrips;                 // planes per full wave of pass A / C
+    if (chunk >= wave && wave > 0) chunk = (chunk / wave) * wave;
+    p.chunk = chunk < 1 ? 1 : chunk;
+    it = g_plans.emplace(key, p).first;
+  }
+  *out = &it->second;
+  return RAMDSIR_OK;
+}
+
+template <class CFG>
+size_t ws_bytes_for(int planes, int chunk) {
+  const int n = planes < chunk ? planes : chunk;
+  return (size_t)n * CFG::nb * CFG::M * 16;
+}
+
+template <class CFG>
+int run(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, size_t ws_bytes, cudaStream_t st) {
+  MpPlan* pl = nullptr;
+  int rc = get_plan<CFG>(&pl);
+  if (rc) return rc;
+  const int planes = nimg * a.C;
+  if (planes == 0) return RAMDSIR_OK;
+  const size_t need = ws_bytes_for<CFG>(planes, pl->chunk);
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("multi-pass path needs %zu workspace bytes, got %zu", need, ws_bytes);
+    return RAMDSIR_ERR_WORKSPACE;
+  }
+  float4* Zg = reinterpret_cast<float4*>(ws);
+  for (int p0 = 0; p0 < planes; p0 += pl->chunk) {
+    const int n = (planes - p0 < pl->chunk) ? planes - p0 : pl->chunk;
+    ram_mp_pass_a<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(a.src, Zg, pl->tab_ac, p0);
+    if (bank_mode) {
+      ram_mp_pass_b<CFG, true><<<n * (CFG::b + 1), CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, nullptr, nullptr, nullptr, 10, 0, a.C, bank_out, pl->tab_b, p0);
+      count_launch(2);
+    } else {
+      ram_mp_pass_b<CFG, false><<<n * (CFG::b + 1), CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, nullptr, pl->tab_b, p0);
+      ram_mp_pass_c<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(a.src, Zg, a.pidx, a.n_bank, a.C, a.out, a.ep, pl->tab_ac, p0);
+      count_launch(3);
+    }
+  }
+  RD_CUDA(cudaGetLastError());
+  return RAMDSIR_OK;
+}
+}  // namespace
+
+bool multipass_supported(int H, int W, int b) {
+  return (H == 512 && W == 512 && b == 51) || (H == 1024 && W == 1024 && b == 102);
+}
+
+size_t multipass_workspace_bytes(int n_images, int C, int H, int W, int b) {
+  (void)W; (void)b;
+  const int planes = n_images * C;
+  // the chunk size depends on the device's SM count; report the upper bound (72 MB budget / per-plane bytes)
+  if (H == 512) return ws_bytes_for<K512>(planes, (int)((size_t)90 * 1024 * 1024 / ((size_t)512 * 512 * 4 + (size_t)K512::nb * K512::M * 16)));
+  return ws_bytes_for<K1024>(planes, (int)((size_t)90 * 1024 * 1024 / ((size_t)1024 * 1024 * 4 + (size_t)K1024::nb * K1024::M * 16)));
+}
+
+int multipass_mix(const MixArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (a.H == 512) return run<K512>(false, a, nullptr, a.B, ws, ws_bytes, st);
+  return run<K1024>(false, a, nullptr, a.B, ws, ws_bytes, st);
+}
+
+int multipass_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, void* ws, size_t ws_bytes, cudaStream_t st) {
+  MixArgs a{};
+  a.src = imgs; a.C = C; a.H = H; a.W = W; a.b = b;
+  if (H == 512) return run<K512>(true, a, bank, N, ws, ws_bytes, st);
+  return run<K1024>(true, a, bank, N, ws, ws_bytes, st);
+}
+
+}  // namespace ramdsir

@@ -46,6 +46,7 @@ static int path_of(int H, int W, int b) {
   const int force = g_force_path.load(std::memory_order_relaxed);
   if (force == RAMDSIR_PATH_GENERIC) return generic_supported(H, W, b) ? RAMDSIR_PATH_GENERIC : RAMDSIR_PATH_NONE;
   if (fused_supported(H, W, b)) return RAMDSIR_PATH_FUSED;
+  if (multipass_supported(H, W, b)) return RAMDSIR_PATH_MULTIPASS;
   if (generic_supported(H, W, b)) return RAMDSIR_PATH_GENERIC;
   return RAMDSIR_PATH_NONE;
 }
@@ -74,6 +75,15 @@ int ramdsir_force_path(int path) {
   return RAMDSIR_OK;
 }
 
+int ramdsir_set_fused_variant(int variant) {
+  if (variant < 0 || variant > 2) {
+    set_error("set_fused_variant: 0 (auto), 1 (P2: one packed column per thread) or 2 (runtime-shape kernel)");
+    return RAMDSIR_ERR_INVALID;
+  }
+  fused_set_variant(variant);
+  return RAMDSIR_OK;
+}
+
 int ramdsir_path(int C, int H, int W, int b) {
   if (check_shape(0, C, H, W, b)) return RAMDSIR_PATH_NONE;
   return path_of(H, W, b);
@@ -81,7 +91,11 @@ int ramdsir_path(int C, int H, int W, int b) {
 
 size_t ramdsir_workspace_bytes(int n_images, int C, int H, int W, int b) {
   if (check_shape(n_images, C, H, W, b)) return 0;
-  return path_of(H, W, b) == RAMDSIR_PATH_GENERIC ? generic_workspace_bytes(n_images, C, H, W, b) : 0;
+  switch (path_of(H, W, b)) {
+    case RAMDSIR_PATH_GENERIC: return generic_workspace_bytes(n_images, C, H, W, b);
+    case RAMDSIR_PATH_MULTIPASS: return multipass_workspace_bytes(n_images, C, H, W, b);
+  }
+  return 0;
 }
 
 int ramdsir_bank_build_f32(const float* imgs_dev, float* bank_dev, int N, int C, int H, int W, int b,
@@ -96,6 +110,7 @@ int ramdsir_bank_build_f32(const float* imgs_dev, float* bank_dev, int N, int C,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (path_of(H, W, b)) {
     case RAMDSIR_PATH_FUSED: return fused_bank(imgs_dev, bank_dev, N, C, H, W, b, st);
+    case RAMDSIR_PATH_MULTIPASS: return multipass_bank(imgs_dev, bank_dev, N, C, H, W, b, workspace_dev, workspace_bytes, st);
     case RAMDSIR_PATH_GENERIC: return generic_bank(imgs_dev, bank_dev, N, C, H, W, b, workspace_dev, workspace_bytes, st);
   }
   set_error("no CUDA path for H=%d W=%d b=%d (and there is no CPU fallback)", H, W, b);
@@ -126,6 +141,7 @@ int ramdsir_mix_f32(const float* src_dev, const float* bank_dev, const int64_t* 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (path_of(H, W, b)) {
     case RAMDSIR_PATH_FUSED: return fused_mix(a, st);
+    case RAMDSIR_PATH_MULTIPASS: return multipass_mix(a, workspace_dev, workspace_bytes, st);
     case RAMDSIR_PATH_GENERIC: return generic_mix(a, workspace_dev, workspace_bytes, st);
   }
   set_error("no CUDA path for H=%d W=%d b=%d (and there is no CPU fallback)", H, W, b);

@@ -52,6 +52,9 @@ def test_path_selection_and_workspace_without_gpu(lib):
     assert lib.ramdsir_path(3, 256, 256, 25) == _lib.PATH_FUSED
     assert lib.ramdsir_path(1, 384, 384, 38) == _lib.PATH_FUSED
     assert lib.ramdsir_path(2, 31, 45, 3) == _lib.PATH_GENERIC
+    assert lib.ramdsir_path(3, 1024, 1024, 102) == _lib.PATH_MULTIPASS
+    assert lib.ramdsir_path(1, 512, 512, 51) == _lib.PATH_MULTIPASS
+    assert lib.ramdsir_workspace_bytes(64, 3, 1024, 1024, 102) > 0
     assert lib.ramdsir_path(3, 64, 64, 40) == _lib.PATH_NONE          # band exceeds the spectrum
     assert lib.ramdsir_workspace_bytes(16, 3, 256, 256, 25) == 0
     assert lib.ramdsir_workspace_bytes(2, 2, 31, 45, 3) == 2 * 2 * (31 * 4 + 7 * 4) * 8

@@ -188,6 +188,31 @@ def test_constant_planes_take_phase_zero_like_the_reference(R, shape):
     check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "constant planes")
 
 
+@pytest.mark.parametrize("variant", [1, 2], ids=["p2", "runtime"])
+@pytest.mark.parametrize("shape", [(3, 256, 256, True), (1, 384, 384, False)], ids=["fundus", "prostate"])
+def test_alternative_fused_variants(R, variant, shape):
+    """The other two implementations of the fused pipeline (selected through ramdsir_set_fused_variant)
+    meet the same tolerance and agree with the default kernels."""
+    from ramdsir_b200 import _lib
+    lib = _lib.load()
+    c, h, w, integer = shape
+    rs = np.random.RandomState(23)
+    lo, hi = (0, 255) if integer else (-1, 1)
+    src = _smooth(rs, (5, c, h, w), lo, hi, integer)
+    par = _smooth(rs, (3, c, h, w), lo, hi, integer)
+    pidx, rk = rs.randint(0, 3, 5), np.array([1, 4, 7, 9, 10], np.int32)
+    epi = O.FUNDUS_EPILOGUE if integer else O.PROSTATE_EPILOGUE
+    base, bank0 = gpu_mix(R, src, par, pidx, rk, 0.1, epi)
+    _lib.check(lib.ramdsir_set_fused_variant(variant))
+    try:
+        got, bank = gpu_mix(R, src, par, pidx, rk, 0.1, epi)
+    finally:
+        lib.ramdsir_set_fused_variant(0)
+    check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "variant %d" % variant)
+    check(got, base, "variant %d vs default" % variant)
+    assert O.rel_l2(bank, bank0) <= 1e-6
+
+
 def test_generic_and_fused_paths_agree(R):
     rs = np.random.RandomState(9)
     src = _smooth(rs, (6, 3, 256, 256), 0, 255, True)
@@ -322,8 +347,31 @@ def test_full_size_prostate_batch(R):
     _amp_identity(R, 512, 1, 384, 384, 64, 1338)            # BASELINE config 3
 
 
+@pytest.mark.parametrize("shape", [(2, 512, 512, True), (1, 1024, 1024, True), (3, 1024, 1024, False)],
+                         ids=["512", "1024", "1024x3_pm1"])
+def test_multipass_oracle_parity(R, shape):
+    """K2 (band buffers in an L2-resident workspace) against the numpy oracle at full image size."""
+    from ramdsir_b200 import _lib
+    c, h, w, integer = shape
+    assert R.kernel_path(c, h, w, R.band_halfwidth(h, w, 0.1)) == _lib.PATH_MULTIPASS
+    rs = np.random.RandomState(h + c)
+    lo, hi = (0, 255) if integer else (-1, 1)
+    src = _smooth(rs, (3, c, h, w), lo, hi, integer)
+    par = _smooth(rs, (2, c, h, w), lo, hi, integer)
+    src[2, 0] = 31.0 if integer else -1.0            # a constant plane (background slice)
+    pidx, rk = np.array([1, 0, 1]), np.array([2, 10, 6], np.int32)
+    epi = O.FUNDUS_EPILOGUE if integer else O.PROSTATE_EPILOGUE
+    got, bank = gpu_mix(R, src, par, pidx, rk, 0.1, epi)
+    check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "multipass %s" % (shape,))
+    assert O.rel_l2(bank, O.build_bank(par, 0.1)) <= 1e-6
+    # cross-check against the independent generic kernels (they use direct sums, so the degenerate
+    # constant-plane image is left out: see DESIGN.md "Conditioning note")
+    g, _ = gpu_mix(R, src[:2], par, pidx[:2], rk[:2], 0.1, epi, force_generic=True)
+    check(got[:2], g, "multipass vs generic")
+
+
 def test_hires_1024(R):
-    _amp_identity(R, 4, 3, 1024, 1024, 3, 1339)             # BASELINE config 5 shape (reduced batch)
+    _amp_identity(R, 24, 3, 1024, 1024, 5, 1339)            # BASELINE config 5 shape, spans several L2 chunks
 
 
 def test_host_pipeline_matches_device_path(R):

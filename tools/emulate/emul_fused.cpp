@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 #include "ram_fused_host.h"
+#include "ram_multipass_host.h"
 
 using namespace ramdsir;
 
@@ -147,6 +148,166 @@ extern "C" int emul_fused_static_smem_bytes(int H, int W, int b) {
   if (H == 256 && W == 256 && b == 25) return SCfg<256, 256, 25>::smemBytes;
   if (H == 384 && W == 384 && b == 38) return SCfg<384, 384, 38>::smemBytes;
   return -1;
+}
+
+// ---- P2 pipeline (one packed column per thread) -------------------------------------------------
+template <class CFG>
+static void run_plane_p2(unsigned char* sm, const float* x, const float* patch, float omr, float* y, Epilogue ep,
+                         float* bank_out) {
+  auto ld = [&](size_t off) { return make_float2(x[2 * off], x[2 * off + 1]); };
+  auto st = [&](size_t off, float2 v) { y[2 * off] = v.x; y[2 * off + 1] = v.y; };
+  constexpr int NT = CFG::nthreads;
+  std::vector<cf> regs((size_t)NT * 16);
+  auto V = [&](int t) -> cf(&)[16] { return *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 16]); };
+  for (int strip = 0; strip < CFG::nstrips; ++strip) {
+    for (int t = 0; t < NT; ++t) p_f1_load_fft_tw<CFG>(ld, sm, strip, t, V(t));
+    for (int half = 0; half < 2; ++half) {
+      for (int t = 0; t < NT; ++t) p_f1_store_half<CFG>(sm, t, half, V(t));
+      for (int u = 0; u < 256; ++u) p_f1_pruned<CFG, 0>(sm, strip, half, u);
+      for (int u = 0; u < 256; ++u) p_f1_pruned<CFG, 1>(sm, strip, half, u);
+    }
+  }
+  for (int r = 0; r < CFG::nb * CFG::N1w; ++r) p_row_fwd<CFG>(sm, r);
+  if (bank_out) {
+    for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) p_band_amp<CFG>(sm, bank_out, q);
+    return;
+  }
+  for (int i = 0; i < CFG::nb * CFG::nb; ++i) s_stage_patch<CFG>(sm, patch, i);
+  for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) p_band_mix<CFG>(sm, omr, q);
+  for (int r = 0; r < CFG::nb * CFG::N1w; ++r) p_row_inv<CFG>(sm, r);
+  for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
+    for (int par = 0; par < 2; ++par) {
+      for (int u = 0; u < 256; ++u) p_inv_pruned<CFG, 0>(sm, strip, par, u);
+      for (int u = 0; u < 256; ++u) p_inv_pruned<CFG, 1>(sm, strip, par, u);
+      for (int t = 0; t < NT; ++t) p_inv_fft8<CFG>(sm, t, par, *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 16 + 8 * par]));
+    }
+    for (int t = 0; t < NT; ++t) {
+      cf* r = &regs[(size_t)t * 16];
+      p_inv_combine_store<CFG>(ld, st, ep, strip, t, *reinterpret_cast<cf(*)[8]>(r), *reinterpret_cast<cf(*)[8]>(r + 8));
+    }
+  }
+}
+
+template <class CFG>
+static int run_all_p2(const float* src, const float* bank, const long long* pidx, const int* rk, int den, float* out,
+                      int B, int C, Epilogue ep, float* bank_out) {
+  std::vector<unsigned char> sm(CFG::smemBytes);
+  fused_tables_fill_p2<CFG>(reinterpret_cast<float*>(sm.data() + CFG::offTab));
+  const size_t plane = (size_t)CFG::H * CFG::W, psz = (size_t)CFG::nb * CFG::nb;
+  for (int i = 0; i < B; ++i)
+    for (int c = 0; c < C; ++c) {
+      const size_t p = (size_t)i * C + c;
+      if (bank_out) { run_plane_p2<CFG>(sm.data(), src + p * plane, nullptr, 0.f, nullptr, ep, bank_out + p * psz); continue; }
+      const float omr = (float)(den - rk[i]) / (float)den;
+      run_plane_p2<CFG>(sm.data(), src + p * plane, bank + ((size_t)pidx[i] * C + c) * psz, omr, out + p * plane, ep, nullptr);
+    }
+  return 0;
+}
+
+extern "C" int emul_fused_p2(const float* src, const float* bank, const long long* pidx, const int* rk, int den,
+                             float* out, int B, int C, int H, int W, int b, float lo, float hi, float scale, float shift,
+                             float* bank_out) {
+  Epilogue ep{lo, hi, scale, shift};
+  if (H == 256 && W == 256 && b == 25) return run_all_p2<PCfg<256, 256, 25>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+  if (H == 384 && W == 384 && b == 38) return run_all_p2<PCfg<384, 384, 38>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+  return 1;
+}
+
+extern "C" int emul_fused_p2_smem_bytes(int H, int W, int b) {
+  if (H == 256 && W == 256 && b == 25) return PCfg<256, 256, 25>::smemBytes;
+  if (H == 384 && W == 384 && b == 38) return PCfg<384, 384, 38>::smemBytes;
+  return -1;
+}
+
+// ---- multi-pass pipeline (K2) ---------------------------------------------------------------
+template <class CFG>
+static int run_all_mp(const float* src, const float* bank, const long long* pidx, const int* rk, int den, float* out,
+                      int B, int C, Epilogue ep, float* bank_out) {
+  std::vector<unsigned char> sm(CFG::smemBytes), smb(CFG::bSmemBytes);
+  multipass_tables_ac<CFG>(reinterpret_cast<float*>(sm.data() + CFG::offTab));
+  multipass_tables_b<CFG>(reinterpret_cast<float*>(smb.data() + CFG::bOffTab));
+  const size_t plane_px = (size_t)CFG::H * CFG::W, psz = (size_t)CFG::nb * CFG::nb;
+  std::vector<float4> Zg((size_t)CFG::nb * CFG::M);
+  std::vector<cf> regs((size_t)256 * 32);
+  for (int i = 0; i < B; ++i)
+    for (int c = 0; c < C; ++c) {
+      const size_t pl = (size_t)i * C + c;
+      const float* x = src + pl * plane_px;
+      auto ld = [&](size_t off) { const float* q = x + 4 * off; return make_float4(q[0], q[1], q[2], q[3]); };
+      // pass A
+      for (int strip = 0; strip < CFG::nstrips; ++strip) {
+        for (int p = 0; p < CFG::HP; ++p) {
+          for (int t = 0; t < 256; ++t)
+            m_f1_load_fft_tw<CFG>(ld, sm.data(), strip, p, t, *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]),
+                                  *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32 + 16]));
+          for (int half = 0; half < 2; ++half) {
+            for (int t = 0; t < 256; ++t)
+              s_f1_store_half<CFG>(sm.data(), t, half, *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]),
+                                   *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32 + 16]));
+            for (int u = 0; u < 256; ++u) m_f1_pruned<CFG>(sm.data(), p, half, u);
+          }
+        }
+        const float4* Zs = reinterpret_cast<const float4*>(sm.data() + CFG::offZ);
+        for (int k = 0; k < CFG::nb; ++k)
+          for (int cc = 0; cc < 16; ++cc) Zg[(size_t)k * CFG::M + strip * 16 + cc] = Zs[k * CFG::pitchZ + cc];
+      }
+      // pass B
+      const float omr = bank_out ? 0.f : (float)(den - rk[i]) / (float)den;
+      const float* patch = bank_out ? nullptr : bank + ((size_t)pidx[i] * C + c) * psz;
+      for (int kh = 0; kh <= CFG::b; ++kh) {
+        const int nrows = kh == 0 ? 1 : 2;
+        float4* R = reinterpret_cast<float4*>(smb.data() + CFG::bOffR);
+        const int rows[2] = {CFG::b + kh, CFG::b - kh};
+        for (int r = 0; r < nrows; ++r)
+          for (int m = 0; m < CFG::M; ++m) R[r * CFG::rowPitch + m] = Zg[(size_t)rows[r] * CFG::M + m];
+        for (int t = 0; t < nrows * CFG::N1w; ++t) m_row_stage1<CFG, -1>(smb.data(), t);
+        for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, -1>(smb.data(), t);
+        if (bank_out) {
+          for (int t = 0; t < nrows * (CFG::b + 1); ++t)
+            m_band<CFG, true>(smb.data(), nullptr, bank_out + pl * psz, 0.f, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+          continue;
+        }
+        for (int t = 0; t < nrows * (CFG::b + 1); ++t)
+          m_band<CFG, false>(smb.data(), patch, nullptr, omr, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+        for (int t = 0; t < nrows * CFG::M; ++t) m_fill_v<CFG>(smb.data(), kh, t / CFG::M, t % CFG::M);
+        for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, 1>(smb.data(), t);
+        for (int t = 0; t < nrows * CFG::N1w; ++t) m_row_stage1<CFG, 1>(smb.data(), t);
+        for (int r = 0; r < nrows; ++r)
+          for (int m = 0; m < CFG::M; ++m) Zg[(size_t)rows[r] * CFG::M + m] = R[r * CFG::rowPitch + m];
+      }
+      if (bank_out) continue;
+      // pass C
+      float* y = out + pl * plane_px;
+      auto st = [&](size_t off, float4 v) { float* q = y + 4 * off; q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w; };
+      for (int strip = 0; strip < CFG::nstrips; ++strip) {
+        float4* Zs = reinterpret_cast<float4*>(sm.data() + CFG::offZ);
+        for (int k = 0; k < CFG::nb; ++k)
+          for (int cc = 0; cc < 16; ++cc) Zs[k * CFG::pitchZ + cc] = Zg[(size_t)k * CFG::M + strip * 16 + cc];
+        for (int p = 0; p < CFG::HP; ++p) {
+          for (int par = 0; par < 2; ++par) {
+            for (int u = 0; u < 256; ++u) m_inv_pruned<CFG>(sm.data(), p, par, u);
+            for (int t = 0; t < 256; ++t)
+              s_inv_fft8<CFG>(sm.data(), t, par, *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 32 + 16 * par]),
+                              *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 32 + 16 * par + 8]));
+          }
+          for (int t = 0; t < 256; ++t) {
+            cf* r = &regs[(size_t)t * 32];
+            MCombine<CFG, 0>::run(ld, st, ep, t >> 4, p, strip * 16 + (t & 15), *reinterpret_cast<cf(*)[8]>(r),
+                                  *reinterpret_cast<cf(*)[8]>(r + 8), *reinterpret_cast<cf(*)[8]>(r + 16), *reinterpret_cast<cf(*)[8]>(r + 24));
+          }
+        }
+      }
+    }
+  return 0;
+}
+
+extern "C" int emul_multipass(const float* src, const float* bank, const long long* pidx, const int* rk, int den,
+                              float* out, int B, int C, int H, int W, int b, float lo, float hi, float scale, float shift,
+                              float* bank_out) {
+  Epilogue ep{lo, hi, scale, shift};
+  if (H == 512 && W == 512 && b == 51) return run_all_mp<KCfg<512, 512, 51>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+  if (H == 1024 && W == 1024 && b == 102) return run_all_mp<KCfg<1024, 1024, 102>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
+  return 1;
 }
 
 extern "C" int emul_fused_smem_bytes(int H, int W, int b) {
