@@ -67,6 +67,58 @@ def _ref_mix(mod, src_chw, trg_chw, L, seed, f64=True):
     return np.ascontiguousarray(out), k, amp
 
 
+def gen_dataset_goldens(fundus, prostate):
+    """Run the reference's OWN dataset classes (Fundus_Multi fundus.py:128-242, Prostate_Multi
+    prostate.py:121-212) on the synthetic fixtures of tests/fixture_data.py and record, per sample, the
+    returned tensors (sub-sampled to keep the fixture small) and the next draw of both RNG streams after
+    the call (proves equal RNG consumption)."""
+    import tempfile
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    import fixture_data as FX
+
+    def after_state():
+        return np.array([random.random(), np.random.rand()])
+
+    with tempfile.TemporaryDirectory() as tmp:
+        froot = FX.make_fundus(os.path.join(tmp, "fundus"))
+        out = {}
+        for tag, kw in (("in", dict(is_out_domain=False)), ("out", dict(is_out_domain=True))):
+            ds = fundus.Fundus_Multi(domain_idx_list=[0, 1, 2], base_dir=froot, split="train", transform=FX.ResizeJitter(),
+                                     test_domain_idx=3, **kw)
+            for i in (0, 4, 9):
+                np.random.seed(100 + i)
+                random.seed(100 + i)
+                torch.manual_seed(0)
+                img, img_freq, mask = ds[i]
+                key = "fundus_%s_%d" % (tag, i)
+                out[key + "_img"] = img.numpy()[:, ::8, ::8]
+                out[key + "_freq"] = img_freq.numpy()[:, ::4, ::4]
+                out[key + "_mask"] = mask.numpy()[:, ::8, ::8]
+                out[key + "_sums"] = np.array([img.double().sum().item(), img_freq.double().sum().item(), mask.double().sum().item()])
+                out[key + "_after"] = after_state()
+        proot = FX.make_prostate(os.path.join(tmp, "prostate"))
+        real_listdir = os.listdir
+        os.listdir = lambda p: sorted(real_listdir(p))      # prostate.py:134,183 depend on directory order
+        try:
+            ds = prostate.Prostate_Multi(domain_idx_list=[0, 1, 2, 3, 4], base_dir=proot, split="train", test_domain_idx=5,
+                                         is_out_domain=True)
+            for i in (0, 7, 13):
+                np.random.seed(200 + i)
+                random.seed(200 + i)
+                img, img_freq, mask = ds[i]
+                key = "prostate_%d" % i
+                out[key + "_img"] = img.numpy()[:, ::8, ::8]
+                out[key + "_freq"] = img_freq.numpy()[:, ::4, ::4]
+                out[key + "_mask"] = mask.numpy()[::8, ::8]
+                out[key + "_sums"] = np.array([img.double().sum().item(), img_freq.double().sum().item(), mask.double().sum().item()])
+                out[key + "_after"] = after_state()
+                out[key + "_dtypes"] = np.array([str(img.dtype), str(img_freq.dtype), str(mask.dtype)])
+        finally:
+            os.listdir = real_listdir
+        np.savez_compressed(os.path.join(OUT, "ram_datasets.npz"), **out)
+
+
 def main():
     fundus, prostate = _load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -145,6 +197,8 @@ def main():
     out, k, _ = _ref_mix(fundus, src, trg, 0.01, seed=7)
     kat["dc_src"], kat["dc_trg"], kat["dc_out"], kat["dc_k"] = src, trg, out, np.array(k)
     np.savez_compressed(os.path.join(OUT, "ram_kats.npz"), **kat)
+
+    gen_dataset_goldens(fundus, prostate)
 
     for f in sorted(os.listdir(OUT)):
         print("%-24s %8.1f KiB" % (f, os.path.getsize(os.path.join(OUT, f)) / 1024))
