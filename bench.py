@@ -257,7 +257,8 @@ def run_ours(args, rank, local_rank, world):
     b = R.band_halfwidth(H, W, L)
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     src = synth(torch, (BATCH, C, H, W), dev, g)
-    out = torch.empty_like(src)
+    outs = [torch.empty_like(src) for _ in range(2)]    # consecutive steps write alternate buffers
+    out = outs[0]
 
     # amplitude bank: built sharded (each rank its rows), replicated once by an all-gather
     lo, hi = sharded.shard_range(N_BANK, rank, world)
@@ -280,8 +281,16 @@ def run_ours(args, rank, local_rank, world):
     pidx, rk = torch.from_numpy(pidx_h).to(dev), torch.from_numpy(rk_h).to(dev)
     epi = R.FUNDUS_EPILOGUE if EPI_NAME == "fundus" else R.PROSTATE_EPILOGUE
 
+    # Steps are independent batches (own output buffer each), as in a loader pipeline that keeps two
+    # batches in flight: the launch is flagged RAMDSIR_FLAG_INDEPENDENT so it may start on SMs that the
+    # previous launch has already vacated (--serial disables that).
+    state = {"i": 0}
+
     def step():
-        R.ram_mix_batch(src, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=out)
+        o = outs[state["i"] & 1]
+        state["i"] += 1
+        R.ram_mix_batch(src, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=o,
+                        independent=not args.serial)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -300,6 +309,16 @@ def run_ours(args, rank, local_rank, world):
         dist.barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
+    # the same K steps with plain stream-ordered launches (reported next to the headline for transparency)
+    serial_ms = None
+    if not args.serial:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            R.ram_mix_batch(src, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=outs[0])
+        e1.record()
+        torch.cuda.synchronize()
+        serial_ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -321,7 +340,7 @@ def run_ours(args, rank, local_rank, world):
         for _ in range(e2e_steps):
             pipe.mix(src_h, bank, pidx_h, rk_h, out_h, epilogue=epi)
         e2e_s = time.perf_counter() - t0
-    same = bool(torch.equal(out_h, out.cpu()))
+    same = bool(torch.equal(out_h, outs[0].cpu())) and bool(torch.equal(outs[0], outs[1]))
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -342,10 +361,17 @@ def run_ours(args, rank, local_rank, world):
                        "l2": "inputs %.0f MB + outputs %.0f MB per step exceed the 126 MB L2 (no flush needed)"
                              % (src.numel() * 4 / 1e6, src.numel() * 4 / 1e6),
                        "parallelism": "batch-sharded x%d, bank all-gather once" % world,
+                       "launch_overlap": "off (--serial)" if args.serial else
+                       "consecutive steps are independent batches (alternating output buffers) launched with "
+                       "RAMDSIR_FLAG_INDEPENDENT: a step may start on SMs the previous step has vacated",
                        "kernel_path": {1: "fused", 2: "multipass", 3: "generic"}.get(R.kernel_path(C, H, W, b))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes, "kernel_ms": kernel_s * 1e3},
+            "serial": None if serial_ms is None else {
+                "ms_per_step": serial_ms, "value": BATCH / (serial_ms * 1e-3),
+                "frac": abytes / (serial_ms * 1e-3) / 1e9 / peak,
+                "note": "rank 0, same K steps launched strictly stream-ordered (no overlap between steps)"},
             "fft_tflops_nominal": nominal_fft_flops_per_image(C, H, W) * value / 1e12,
             "e2e": {"value": e2e_value, "unit": "images/s",
                     "h2d_bytes_per_step": int(src_h.numel() * 4 + pidx_h.nbytes + rk_h.nbytes),
@@ -374,6 +400,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--serial", action="store_true", help="plain stream-ordered launches (no overlap between steps)")
     ap.add_argument("--no-e2e", action="store_true", help="(dev) shorten the host-buffer end-to-end leg to one step")
     ap.add_argument("--workload", default="fundus", choices=sorted(WORKLOADS), help="(dev) default = BASELINE configs[1]")
     args = ap.parse_args()

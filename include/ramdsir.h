@@ -86,6 +86,20 @@ int ramdsir_mix_f32(const float* src_dev, const float* bank_dev, const int64_t* 
                     void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /*
+ * Same as ramdsir_mix_f32 with flags.  RAMDSIR_FLAG_INDEPENDENT: the caller promises that this call does
+ * not read or overwrite anything produced by the kernel that precedes it in `stream` (consecutive batches
+ * of a loader pipeline, each with its own input and output buffers).  The fused path then launches with
+ * programmatic stream serialisation, so this launch starts occupying SMs while the previous RAM launch
+ * drains its last wave instead of waiting for it to finish.  Ordering against copies and against every
+ * other kernel is unchanged.  Without the flag the call is plainly stream-ordered.
+ */
+#define RAMDSIR_FLAG_INDEPENDENT 1u
+int ramdsir_mix_f32_ex(const float* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
+                       const int32_t* ratio_k_dev, float* out_dev, int B, int C, int H, int W, int b,
+                       int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
+                       void* workspace_dev, size_t workspace_bytes, void* stream, unsigned flags);
+
+/*
  * Strict per-sample drop-ins (correctness shims for code that calls the reference functions directly).
  *   ramdsir_amp_spectrum_f32 <- extract_amp_spectrum: FULL amplitude spectrum [N, C, H, W], un-shifted
  *                               (fundus.py:13-19).  Direct DFT, any H and W; workspace from

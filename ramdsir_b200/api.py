@@ -109,13 +109,17 @@ def _index_tensor(x, dtype, device, name, lo=None, hi=None):
 def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L: float = 0.1,
                   clip=(-math.inf, math.inf), scale: float = 1.0, shift: float = 0.0,
                   out: torch.Tensor | None = None, ratio_den: int = 10, stream=None,
-                  workspace: torch.Tensor | None = None) -> torch.Tensor:
+                  workspace: torch.Tensor | None = None, independent: bool = False) -> torch.Tensor:
     """Random Amplitude Mixup of a batch (K1/K2).
 
     src [B, C, H, W] float32 CUDA; bank [N, C, 2b+1, 2b+1] from `build_amp_bank`;
     partner_idx [B] int (indices into the bank); ratio_k [B] int, ratio = ratio_k / ratio_den is the
     weight of the SOURCE amplitude (fundus.py:35,37; the reference draws ratio_k = randint(1, 10)).
     Returns clamp(RAM(src), clip) * scale + shift, float32 [B, C, H, W].
+
+    independent=True promises that this call neither reads nor overwrites anything the previous kernel on
+    the stream produced (back-to-back batches with their own buffers); the launch may then overlap the tail
+    of the previous RAM launch (RAMDSIR_FLAG_INDEPENDENT in include/ramdsir.h).
     """
     src = _need_cuda_f32(src, "src", 4)
     bank = _need_cuda_f32(bank, "bank", 4)
@@ -141,10 +145,11 @@ def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L
     lib = _lib.load()
     with torch.cuda.device(src.device):
         ws, ws_ptr, ws_n = _workspace(workspace_bytes(bsz, c, h, w, b), src.device, workspace)
-        _lib.check(lib.ramdsir_mix_f32(src.data_ptr(), bank.data_ptr(), pidx.data_ptr(), rk.data_ptr(),
-                                       out.data_ptr(), bsz, c, h, w, b, n_bank, int(ratio_den),
-                                       float(clip[0]), float(clip[1]), float(scale), float(shift),
-                                       ws_ptr, ws_n, _stream_ptr(stream)))
+        _lib.check(lib.ramdsir_mix_f32_ex(src.data_ptr(), bank.data_ptr(), pidx.data_ptr(), rk.data_ptr(),
+                                          out.data_ptr(), bsz, c, h, w, b, n_bank, int(ratio_den),
+                                          float(clip[0]), float(clip[1]), float(scale), float(shift),
+                                          ws_ptr, ws_n, _stream_ptr(stream),
+                                          _lib.FLAG_INDEPENDENT if independent else 0))
         cur = torch.cuda.current_stream() if stream is None else stream
         for t in (pidx, rk, ws):
             if t is not None:

@@ -114,6 +114,8 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
   extern __shared__ __align__(16) unsigned char sm[];
   constexpr int NT = CFG::nthreads;
   const int tid = threadIdx.x;
+  // let a launch that was declared independent (RAMDSIR_FLAG_INDEPENDENT) take over SM slots as ours drain
+  asm volatile("griddepcontrol.launch_dependents;");
   unsigned long long pol_keep, pol_stream;
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
@@ -215,6 +217,8 @@ ram_fused_p2_kernel(const float* __restrict__ src, const float* __restrict__ ban
   extern __shared__ __align__(16) unsigned char sm[];
   constexpr int NT = CFG::nthreads;
   const int tid = threadIdx.x;
+  // let a launch that was declared independent (RAMDSIR_FLAG_INDEPENDENT) take over SM slots as ours drain
+  asm volatile("griddepcontrol.launch_dependents;");
   unsigned long long pol_keep, pol_stream;
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
@@ -310,6 +314,7 @@ using Cfg256 = SCfg<256, 256, 25>;
 using Cfg384 = SCfg<384, 384, 38>;
 using P256 = PCfg<256, 256, 25>;
 using P384 = PCfg<384, 384, 38>;
+thread_local int t_overlap = 0;   // per-call flag of the calling thread (set by fused_mix, read by launch_static)
 std::atomic<int> g_variant{0};   // RAMDSIR_VARIANT_*: 0 auto (= float4 static kernels), 1 P2, 2 runtime-shape
 int static_id_of(int H, int W, int b, int variant) {
   if (variant == 2) return 0;
@@ -394,7 +399,22 @@ int launch_static(const FusedPlan& p, const float* src, const float* bank, const
   }
   int grid = p.sm_count * per_sm;
   if (grid > nplanes) grid = nplanes;
-  kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes);
+  if (t_overlap && !BANK) {
+    // programmatic dependent launch: do not wait for the previous kernel in the stream to finish
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(CFG::nthreads);
+    cfg.dynamicSmemBytes = CFG::smemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RD_CUDA(cudaLaunchKernelEx(&cfg, kern, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, (const float*)p.tables, nplanes));
+  } else {
+    kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes);
+  }
   count_launch();
   RD_CUDA(cudaGetLastError());
   return RAMDSIR_OK;
@@ -430,6 +450,7 @@ int fused_mix(const MixArgs& a, cudaStream_t st) {
   FusedPlan* p = nullptr;
   int rc = get_plan(a.H, a.W, a.b, &p);
   if (rc) return rc;
+  t_overlap = a.independent ? 1 : 0;
   return dispatch<false>(*p, a.src, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, a.out, a.ep, a.B * a.C, st);
 }
 

@@ -27,6 +27,7 @@ struct MixArgs {
   float* out;
   int B, C, H, W, b, n_bank, ratio_den;
   Epilogue ep;
+  bool independent = false;   // RAMDSIR_FLAG_INDEPENDENT
 };
 
 // fused single-CTA-per-plane path (ram_fused.cu)

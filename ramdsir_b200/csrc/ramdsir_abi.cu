@@ -121,6 +121,14 @@ int ramdsir_mix_f32(const float* src_dev, const float* bank_dev, const int64_t* 
                     const int32_t* ratio_k_dev, float* out_dev, int B, int C, int H, int W, int b,
                     int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return ramdsir_mix_f32_ex(src_dev, bank_dev, partner_idx_dev, ratio_k_dev, out_dev, B, C, H, W, b, n_bank, ratio_den,
+                            clip_lo, clip_hi, scale, shift, workspace_dev, workspace_bytes, stream, 0u);
+}
+
+int ramdsir_mix_f32_ex(const float* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
+                       const int32_t* ratio_k_dev, float* out_dev, int B, int C, int H, int W, int b,
+                       int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
+                       void* workspace_dev, size_t workspace_bytes, void* stream, unsigned flags) {
   int rc = check_shape(B, C, H, W, b);
   if (rc) return rc;
   if (B == 0) return RAMDSIR_OK;
@@ -138,6 +146,7 @@ int ramdsir_mix_f32(const float* src_dev, const float* bank_dev, const int64_t* 
   }
   MixArgs a{src_dev, bank_dev, partner_idx_dev, ratio_k_dev, out_dev, B, C, H, W, b, n_bank, ratio_den,
             Epilogue{clip_lo, clip_hi, scale, shift}};
+  a.independent = (flags & RAMDSIR_FLAG_INDEPENDENT) != 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (path_of(H, W, b)) {
     case RAMDSIR_PATH_FUSED: return fused_mix(a, st);
