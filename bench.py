@@ -255,6 +255,8 @@ def run_ours(args, rank, local_rank, world):
     from ramdsir_b200.host import HostPipeline
 
     b = R.band_halfwidth(H, W, L)
+    if args.variant:
+        _lib.check(_lib.load().ramdsir_set_fused_variant(args.variant))
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     src = synth(torch, (BATCH, C, H, W), dev, g)
     outs = [torch.empty_like(src) for _ in range(2)]    # consecutive steps write alternate buffers
@@ -400,6 +402,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--variant", type=int, default=0, help="(dev) ramdsir_set_fused_variant")
     ap.add_argument("--serial", action="store_true", help="plain stream-ordered launches (no overlap between steps)")
     ap.add_argument("--no-e2e", action="store_true", help="(dev) shorten the host-buffer end-to-end leg to one step")
     ap.add_argument("--workload", default="fundus", choices=sorted(WORKLOADS), help="(dev) default = BASELINE configs[1]")
