@@ -6,6 +6,10 @@
 #include "ram_internal.h"
 #include "ram_multipass_host.h"
 
+#ifndef RAMDSIR_MP_CHUNK_MB
+#define RAMDSIR_MP_CHUNK_MB 90   // x + band workspace of one chunk of planes (measured: 18-plane chunks beat 9-plane chunks, 56k vs 42k img/s)
+#endif
+
 namespace ramdsir {
 
 __device__ __forceinline__ float4 mp_ldg_policy(const float4* p, unsigned long long pol) {
@@ -51,33 +55,52 @@ ram_mp_pass_a(const float* __restrict__ src, float4* __restrict__ Zg, const floa
   for (int i = tid; i < CFG::nb * 16; i += 256) zg[(size_t)(i >> 4) * CFG::M + (i & 15)] = Zs[(i >> 4) * CFG::pitchZ + (i & 15)];
 }
 
-// ---- pass B: rows +kh and -kh of one plane: row FFTs, band update, inverse row FFTs, in place ---------
+// ---- pass B: KG pairs of rows (+kh, -kh) of one plane: row FFTs, band update, inverse row FFTs, in place ----
 template <class CFG, bool BANK>
 __global__ void __launch_bounds__(CFG::bThreads)
 ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank, const int64_t* __restrict__ pidx,
               const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ bank_out,
               const float* __restrict__ tables, int plane0) {
   extern __shared__ __align__(16) unsigned char sm[];
-  constexpr int NT = CFG::bThreads;
-  const int tid = threadIdx.x, kh = blockIdx.x % (CFG::b + 1), lp = blockIdx.x / (CFG::b + 1);
-  const int plane = plane0 + lp, nrows = (kh == 0) ? 1 : 2;
+  constexpr int NT = CFG::bThreads, KG = CFG::KG, M = CFG::M, RP = 2 * CFG::rowPitch, DP = 2 * (CFG::b + 1);
+  const int tid = threadIdx.x, kh0 = (blockIdx.x % CFG::nkg) * KG, lp = blockIdx.x / CFG::nkg;
+  const int plane = plane0 + lp;
+  const int ng = (CFG::b + 1 - kh0 < KG) ? CFG::b + 1 - kh0 : KG;     // kh values handled here
   {
-    float4* tab = reinterpret_cast<float4*>(sm + CFG::bOffTab);
+    float4* tab4 = reinterpret_cast<float4*>(sm + CFG::bOffTab);
     const float4* g = reinterpret_cast<const float4*>(tables);
-    for (int i = tid; i < CFG::bTabBytes / 16; i += NT) tab[i] = g[i];
+    for (int i = tid; i < CFG::bTabBytes / 16; i += NT) tab4[i] = g[i];
   }
   float4* R = reinterpret_cast<float4*>(sm + CFG::bOffR);
-  float4* zrow[2] = {Zg + ((size_t)lp * CFG::nb + (CFG::b + kh)) * CFG::M, Zg + ((size_t)lp * CFG::nb + (CFG::b - kh)) * CFG::M};
-  for (int i = tid; i < nrows * CFG::M; i += NT) R[(i / CFG::M) * CFG::rowPitch + (i % CFG::M)] = zrow[i / CFG::M][i % CFG::M];
+  float2* D = reinterpret_cast<float2*>(sm + CFG::bOffD);
+  const float* tab = reinterpret_cast<const float*>(sm + CFG::bOffTab);
+  float4* zplane = Zg + (size_t)lp * CFG::nb * M;
+  // row slot r = 2 g + s  <->  band row  b + kh (s = 0)  /  b - kh (s = 1),  kh = kh0 + g  (kh = 0 uses s = 0 only)
+  auto zrow = [&](int r) { const int kh = kh0 + (r >> 1); return zplane + (size_t)(CFG::b + ((r & 1) ? -kh : kh)) * M; };
+  auto live = [&](int r) { return !((r & 1) && kh0 + (r >> 1) == 0); };
+  for (int i = tid; i < ng * 2 * M; i += NT) {
+    const int r = i / M, m = i % M;
+    if (live(r)) R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + m] = zrow(r)[m];
+  }
   __syncthreads();
-  for (int t = tid; t < nrows * CFG::N1w; t += NT) m_row_stage1<CFG, -1>(sm, t);
+  for (int t = tid; t < ng * 2 * CFG::N1w; t += NT) {
+    const int g = t / (2 * CFG::N1w), tt = t % (2 * CFG::N1w);
+    if (live(2 * g + tt / CFG::N1w)) m_row_stage1<CFG, -1>(R + (size_t)g * RP, tab, tt);
+  }
   __syncthreads();
-  for (int t = tid; t < nrows * 16; t += NT) m_row_stage2<CFG, -1>(sm, t);
+  for (int t = tid; t < ng * 32; t += NT) {
+    const int g = t / 32, tt = t % 32;
+    if (live(2 * g + tt / 16)) m_row_stage2<CFG, -1>(R + (size_t)g * RP, tt);
+  }
   __syncthreads();
   const size_t patch_px = (size_t)CFG::nb * CFG::nb;
+  const int nband = 2 * (CFG::b + 1);
   if (BANK) {
     float* patch = bank_out + (size_t)plane * patch_px;
-    for (int t = tid; t < nrows * (CFG::b + 1); t += NT) m_band<CFG, true>(sm, nullptr, patch, 0.f, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+    for (int t = tid; t < ng * nband; t += NT) {
+      const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
+      if (live(2 * g + srow)) m_band<CFG, true>(R + (size_t)g * RP, D + g * DP, tab, nullptr, patch, 0.f, kh0 + g, srow, tt % (CFG::b + 1));
+    }
     return;
   }
   {
@@ -86,16 +109,31 @@ ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank, const int
     const bool ok = (p >= 0 && p < (long long)n_bank);
     const float omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
     const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
-    for (int t = tid; t < nrows * (CFG::b + 1); t += NT) m_band<CFG, false>(sm, patch, nullptr, omr, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+    for (int t = tid; t < ng * nband; t += NT) {
+      const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
+      if (live(2 * g + srow)) m_band<CFG, false>(R + (size_t)g * RP, D + g * DP, tab, patch, nullptr, omr, kh0 + g, srow, tt % (CFG::b + 1));
+    }
   }
   __syncthreads();
-  for (int t = tid; t < nrows * CFG::M; t += NT) m_fill_v<CFG>(sm, kh, t / CFG::M, t % CFG::M);
+  for (int t = tid; t < ng * 2 * M; t += NT) {
+    const int g = t / (2 * M), tt = t % (2 * M);
+    if (live(2 * g + tt / M)) m_fill_v<CFG>(R + (size_t)g * RP, D + g * DP, tab, kh0 + g, tt / M, tt % M);
+  }
   __syncthreads();
-  for (int t = tid; t < nrows * 16; t += NT) m_row_stage2<CFG, 1>(sm, t);
+  for (int t = tid; t < ng * 32; t += NT) {
+    const int g = t / 32, tt = t % 32;
+    if (live(2 * g + tt / 16)) m_row_stage2<CFG, 1>(R + (size_t)g * RP, tt);
+  }
   __syncthreads();
-  for (int t = tid; t < nrows * CFG::N1w; t += NT) m_row_stage1<CFG, 1>(sm, t);
+  for (int t = tid; t < ng * 2 * CFG::N1w; t += NT) {
+    const int g = t / (2 * CFG::N1w), tt = t % (2 * CFG::N1w);
+    if (live(2 * g + tt / CFG::N1w)) m_row_stage1<CFG, 1>(R + (size_t)g * RP, tab, tt);
+  }
   __syncthreads();
-  for (int i = tid; i < nrows * CFG::M; i += NT) zrow[i / CFG::M][i % CFG::M] = R[(i / CFG::M) * CFG::rowPitch + (i % CFG::M)];
+  for (int i = tid; i < ng * 2 * M; i += NT) {
+    const int r = i / M, m = i % M;
+    if (live(r)) zrow(r)[m] = R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + m];
+  }
 }
 
 // ---- pass C: inverse columns of one (plane, strip), + x, epilogue -------------------------------------
@@ -180,8 +218,8 @@ int get_plan(MpPlan** out) {
     int sms = 148;
     RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t per_plane = (size_t)CFG::H * CFG::W * 4 + (size_t)CFG::nb * CFG::M * 16;
-    int chunk = (int)((size_t)90 * 1024 * 1024 / per_plane);
-    const int wave = 2 * sms / CFG::nstrips;                 // planes per full wave of pass A / C
+    int chunk = (int)((size_t)RAMDSIR_MP_CHUNK_MB * 1024 * 1024 / per_plane);
+    const int wave = 2 * sms / CFG::nstrips;                 // planes per full wave (2 CTAs per SM) of pass A / C
     if (chunk >= wave && wave > 0) chunk = (chunk / wave) * wave;
     p.chunk = chunk < 1 ? 1 : chunk;
     it = g_plans.emplace(key, p).first;
@@ -213,10 +251,10 @@ int run(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, s
     const int n = (planes - p0 < pl->chunk) ? planes - p0 : pl->chunk;
     ram_mp_pass_a<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(a.src, Zg, pl->tab_ac, p0);
     if (bank_mode) {
-      ram_mp_pass_b<CFG, true><<<n * (CFG::b + 1), CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, nullptr, nullptr, nullptr, 10, 0, a.C, bank_out, pl->tab_b, p0);
+      ram_mp_pass_b<CFG, true><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, nullptr, nullptr, nullptr, 10, 0, a.C, bank_out, pl->tab_b, p0);
       count_launch(2);
     } else {
-      ram_mp_pass_b<CFG, false><<<n * (CFG::b + 1), CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, nullptr, pl->tab_b, p0);
+      ram_mp_pass_b<CFG, false><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, nullptr, pl->tab_b, p0);
       ram_mp_pass_c<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(a.src, Zg, a.pidx, a.n_bank, a.C, a.out, a.ep, pl->tab_ac, p0);
       count_launch(3);
     }
@@ -234,8 +272,8 @@ size_t multipass_workspace_bytes(int n_images, int C, int H, int W, int b) {
   (void)W; (void)b;
   const int planes = n_images * C;
   // the chunk size depends on the device's SM count; report the upper bound (72 MB budget / per-plane bytes)
-  if (H == 512) return ws_bytes_for<K512>(planes, (int)((size_t)90 * 1024 * 1024 / ((size_t)512 * 512 * 4 + (size_t)K512::nb * K512::M * 16)));
-  return ws_bytes_for<K1024>(planes, (int)((size_t)90 * 1024 * 1024 / ((size_t)1024 * 1024 * 4 + (size_t)K1024::nb * K1024::M * 16)));
+  if (H == 512) return ws_bytes_for<K512>(planes, (int)((size_t)RAMDSIR_MP_CHUNK_MB * 1024 * 1024 / ((size_t)512 * 512 * 4 + (size_t)K512::nb * K512::M * 16)));
+  return ws_bytes_for<K1024>(planes, (int)((size_t)RAMDSIR_MP_CHUNK_MB * 1024 * 1024 / ((size_t)1024 * 1024 * 4 + (size_t)K1024::nb * K1024::M * 16)));
 }
 
 int multipass_mix(const MixArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {

@@ -38,11 +38,13 @@ struct KCfg {
   static constexpr int tTWP = tTWH + N1h * twhPitch * 2;       // [HP][nb] float2  W_H^(p kh)
   static constexpr int tabBytes = s_al16((tTWP + HP * nb * 2) * 4);
   static constexpr int smemBytes = offTab + tabBytes;
-  // pass B shared memory: two rows of M float4 (+1 pad), D rows, tables
+  // pass B shared memory: KG pairs of rows (+kh, -kh) of M float4 (+1 pad), their D rows, tables
+  static constexpr int KG = 4;                                 // kh values per CTA
+  static constexpr int nkg = (B_ + 1 + KG - 1) / KG;           // CTAs per plane
   static constexpr int rowPitch = M + 1;
-  static constexpr int bOffR = 0;
-  static constexpr int bOffD = s_al16(2 * rowPitch * 16);      // [2][b+1] float2
-  static constexpr int bOffTab = bOffD + s_al16(2 * (B_ + 1) * 8);
+  static constexpr int bOffR = 0;                              // [KG][2][rowPitch] float4
+  static constexpr int bOffD = s_al16(KG * 2 * rowPitch * 16); // [KG][2][b+1] float2
+  static constexpr int bOffTab = bOffD + s_al16(KG * 2 * (B_ + 1) * 8);
   static constexpr int tTWM = 0;                               // [N1w][16] float2  W_M^(c1 k2)
   static constexpr int tTW3 = tTWM + N1w * 16 * 2;             // [3][b+1] float2   W_W^(g kw)
   static constexpr int tQ = ((tTW3 + 3 * (B_ + 1) * 2) + 3) & ~3;   // [nb] float4: (Qa, Qb)[kw]
@@ -191,10 +193,10 @@ struct MCombine<CFG, 8> {
 // ===== pass B ==================================================================================
 // Row FFT stage 1 (c1 fixed): radix-16 over j on slots c1 + N1w j, x TWM[c1][k2], back to slot c1 + N1w k2.
 template <class CFG, int DIR>
-RD_HD void m_row_stage1(unsigned char* sm, int task) {
+RD_HD void m_row_stage1(float4* Rbase, const float* tab, int task) {
   const int row = task / CFG::N1w, c1 = task % CFG::N1w;
-  float4* R = reinterpret_cast<float4*>(sm + CFG::bOffR) + (size_t)row * CFG::rowPitch + c1;
-  const float2* tw = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(sm + CFG::bOffTab) + CFG::tTWM) + c1 * 16;
+  float4* R = Rbase + (size_t)row * CFG::rowPitch + c1;
+  const float2* tw = reinterpret_cast<const float2*>(tab + CFG::tTWM) + c1 * 16;
   cf va[16], vb[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -223,9 +225,9 @@ RD_HD void m_row_stage1(unsigned char* sm, int task) {
 
 // Row FFT stage 2 (k2 fixed): N1w-point FFT over c1 on the contiguous slots N1w k2 + c1 -> bin kw = k2 + 16 q at slot N1w k2 + q.
 template <class CFG, int DIR>
-RD_HD void m_row_stage2(unsigned char* sm, int task) {
+RD_HD void m_row_stage2(float4* Rbase, int task) {
   const int row = task / 16, k2 = task % 16;
-  float4* R = reinterpret_cast<float4*>(sm + CFG::bOffR) + (size_t)row * CFG::rowPitch + CFG::N1w * k2;
+  float4* R = Rbase + (size_t)row * CFG::rowPitch + CFG::N1w * k2;
   cf va[CFG::N1w], vb[CFG::N1w];
 #pragma unroll
   for (int i = 0; i < CFG::N1w; ++i) {
@@ -251,9 +253,8 @@ RD_HD int m_slot(int kw) {
 
 // Band task: bin (s kh, kw), kw in [0, b], s = +1 (row 0 = +kh) or -1 (row 1 = -kh).  Writes D[s][kw].
 template <class CFG, bool BANK>
-RD_HD void m_band(unsigned char* sm, const float* patch, float* patch_out, float one_minus_ratio, int kh, int srow, int kw) {
-  const float4* R = reinterpret_cast<const float4*>(sm + CFG::bOffR);
-  const float* tab = reinterpret_cast<const float*>(sm + CFG::bOffTab);
+RD_HD void m_band(const float4* R, float2* D, const float* tab, const float* patch, float* patch_out, float one_minus_ratio,
+                  int kh, int srow, int kw) {
   const int khs = srow ? -kh : kh;
   const float4 up4 = R[(size_t)srow * CFG::rowPitch + m_slot<CFG>(kw)];
   const float4 um4 = R[(size_t)(kh == 0 ? 0 : 1 - srow) * CFG::rowPitch + m_slot<CFG>(-kw)];
@@ -284,28 +285,27 @@ RD_HD void m_band(unsigned char* sm, const float* patch, float* patch_out, float
     d = cf{one_minus_ratio * at * CFG::invHW, 0.f};
   }
   if (kw == 0 && kh == 0) d.im = 0.f;
-  reinterpret_cast<float2*>(sm + CFG::bOffD)[srow * (CFG::b + 1) + kw] = make_float2(d.re, d.im);
+  D[srow * (CFG::b + 1) + kw] = make_float2(d.re, d.im);
 }
 
 // Fill row `srow` with the inverse-side packed spectrum V{a,b}[kw] = dF[s kh][kw] * (Qa, Qb)[kw] (zero off the band).
 template <class CFG>
-RD_HD void m_fill_v(unsigned char* sm, int kh, int srow, int slot_idx) {
+RD_HD void m_fill_v(float4* R, const float2* D, const float* tab, int kh, int srow, int slot_idx) {
   // slot_idx enumerates the M slots of the row; slot = N1w k2 + q  <->  kw = k2 + 16 q (mod M, centred)
   const int k2 = slot_idx / CFG::N1w, q = slot_idx % CFG::N1w;
   int kw = k2 + 16 * q;
   if (kw >= CFG::M / 2) kw -= CFG::M;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (kw >= -CFG::b && kw <= CFG::b) {
-    const float2* D = reinterpret_cast<const float2*>(sm + CFG::bOffD);
     const int other = (kh == 0) ? 0 : 1 - srow;
     cf d;
     if (kw >= 0) { const float2 t = D[srow * (CFG::b + 1) + kw]; d = cf{t.x, t.y}; }
     else { const float2 t = D[other * (CFG::b + 1) - kw]; d = cf{t.x, -t.y}; }   // dF[-k] = conj dF[k]
-    const float4 qq = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::bOffTab) + CFG::tQ)[kw + CFG::b];
+    const float4 qq = reinterpret_cast<const float4*>(tab + CFG::tQ)[kw + CFG::b];
     const cf a = cmul(d, cf{qq.x, qq.y}), bq = cmul(d, cf{qq.z, qq.w});
     v = make_float4(a.re, a.im, bq.re, bq.im);
   }
-  reinterpret_cast<float4*>(sm + CFG::bOffR)[(size_t)srow * CFG::rowPitch + slot_idx] = v;
+  R[(size_t)srow * CFG::rowPitch + slot_idx] = v;
 }
 
 }  // namespace ramdsir

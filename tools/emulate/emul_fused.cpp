@@ -257,21 +257,23 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
       for (int kh = 0; kh <= CFG::b; ++kh) {
         const int nrows = kh == 0 ? 1 : 2;
         float4* R = reinterpret_cast<float4*>(smb.data() + CFG::bOffR);
+        float2* D = reinterpret_cast<float2*>(smb.data() + CFG::bOffD);
+        const float* tab = reinterpret_cast<const float*>(smb.data() + CFG::bOffTab);
         const int rows[2] = {CFG::b + kh, CFG::b - kh};
         for (int r = 0; r < nrows; ++r)
           for (int m = 0; m < CFG::M; ++m) R[r * CFG::rowPitch + m] = Zg[(size_t)rows[r] * CFG::M + m];
-        for (int t = 0; t < nrows * CFG::N1w; ++t) m_row_stage1<CFG, -1>(smb.data(), t);
-        for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, -1>(smb.data(), t);
+        for (int t = 0; t < nrows * CFG::N1w; ++t) m_row_stage1<CFG, -1>(R, tab, t);
+        for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, -1>(R, t);
         if (bank_out) {
           for (int t = 0; t < nrows * (CFG::b + 1); ++t)
-            m_band<CFG, true>(smb.data(), nullptr, bank_out + pl * psz, 0.f, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+            m_band<CFG, true>(R, D, tab, nullptr, bank_out + pl * psz, 0.f, kh, t / (CFG::b + 1), t % (CFG::b + 1));
           continue;
         }
         for (int t = 0; t < nrows * (CFG::b + 1); ++t)
-          m_band<CFG, false>(smb.data(), patch, nullptr, omr, kh, t / (CFG::b + 1), t % (CFG::b + 1));
-        for (int t = 0; t < nrows * CFG::M; ++t) m_fill_v<CFG>(smb.data(), kh, t / CFG::M, t % CFG::M);
-        for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, 1>(smb.data(), t);
-        for (int t = 0; t < nrows * CFG::N1w; ++t) m_row_stage1<CFG, 1>(smb.data(), t);
+          m_band<CFG, false>(R, D, tab, patch, nullptr, omr, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+        for (int t = 0; t < nrows * CFG::M; ++t) m_fill_v<CFG>(R, D, tab, kh, t / CFG::M, t % CFG::M);
+        for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, 1>(R, t);
+        for (int t = 0; t < nrows * CFG::N1w; ++t) m_row_stage1<CFG, 1>(R, tab, t);
         for (int r = 0; r < nrows; ++r)
           for (int m = 0; m < CFG::M; ++m) Zg[(size_t)rows[r] * CFG::M + m] = R[r * CFG::rowPitch + m];
       }
