@@ -100,6 +100,17 @@ int ramdsir_mix_f32_ex(const float* src_dev, const float* bank_dev, const int64_
                        void* workspace_dev, size_t workspace_bytes, void* stream, unsigned flags);
 
 /*
+ * Dual output (what the train step consumes, train.py:244): besides out = clamp(RAM(src)) * scale + shift, also
+ * write the normalised CLEAN batch clean_out = src * scale + shift (fundus.py:217-218: img /= 127.5; img -= 1.0,
+ * reproduced to 1 ulp).  On the static fused kernels it is produced from the same read of src (no extra pass over
+ * the input); other paths run one extra streaming kernel.  clean_out_dev may be NULL (= ramdsir_mix_f32_ex).
+ */
+int ramdsir_mix_dual_f32(const float* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
+                         const int32_t* ratio_k_dev, float* out_dev, float* clean_out_dev, int B, int C, int H, int W,
+                         int b, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
+                         void* workspace_dev, size_t workspace_bytes, void* stream, unsigned flags);
+
+/*
  * Strict per-sample drop-ins (correctness shims for code that calls the reference functions directly).
  *   ramdsir_amp_spectrum_f32 <- extract_amp_spectrum: FULL amplitude spectrum [N, C, H, W], un-shifted
  *                               (fundus.py:13-19).  Direct DFT, any H and W; workspace from

@@ -23,7 +23,7 @@ PATH_NONE, PATH_FUSED, PATH_MULTIPASS, PATH_GENERIC = 0, 1, 2, 3
 # every symbol include/ramdsir.h declares (tests/test_abi_cpu.py checks the .so exports them all)
 SYMBOLS = [
     "ramdsir_version", "ramdsir_last_error", "ramdsir_band_halfwidth", "ramdsir_path", "ramdsir_force_path", "ramdsir_set_fused_variant",
-    "ramdsir_workspace_bytes", "ramdsir_bank_build_f32", "ramdsir_mix_f32", "ramdsir_mix_f32_ex",
+    "ramdsir_workspace_bytes", "ramdsir_bank_build_f32", "ramdsir_mix_f32", "ramdsir_mix_f32_ex", "ramdsir_mix_dual_f32",
     "ramdsir_amp_spectrum_workspace_bytes", "ramdsir_amp_spectrum_f32", "ramdsir_band_blend_f32",
     "ramdsir_pipe_create", "ramdsir_pipe_destroy", "ramdsir_mix_host_f32", "ramdsir_launch_count",
 ]
@@ -73,6 +73,7 @@ def _declare(lib):
     lib.ramdsir_bank_build_f32.argtypes = [vp, vp] + [c.c_int] * 5 + [vp, c.c_size_t, vp]
     lib.ramdsir_mix_f32.argtypes = ([vp] * 5 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_size_t, vp])
     lib.ramdsir_mix_f32_ex.argtypes = ([vp] * 5 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_size_t, vp, c.c_uint])
+    lib.ramdsir_mix_dual_f32.argtypes = ([vp] * 6 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_size_t, vp, c.c_uint])
     lib.ramdsir_amp_spectrum_workspace_bytes.argtypes = [c.c_int] * 4
     lib.ramdsir_amp_spectrum_workspace_bytes.restype = c.c_size_t
     lib.ramdsir_amp_spectrum_f32.argtypes = [vp, vp] + [c.c_int] * 4 + [vp, c.c_size_t, vp]

@@ -109,13 +109,17 @@ def _index_tensor(x, dtype, device, name, lo=None, hi=None):
 def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L: float = 0.1,
                   clip=(-math.inf, math.inf), scale: float = 1.0, shift: float = 0.0,
                   out: torch.Tensor | None = None, ratio_den: int = 10, stream=None,
-                  workspace: torch.Tensor | None = None, independent: bool = False) -> torch.Tensor:
+                  workspace: torch.Tensor | None = None, independent: bool = False,
+                  clean_out: torch.Tensor | None = None) -> torch.Tensor:
     """Random Amplitude Mixup of a batch (K1/K2).
 
     src [B, C, H, W] float32 CUDA; bank [N, C, 2b+1, 2b+1] from `build_amp_bank`;
     partner_idx [B] int (indices into the bank); ratio_k [B] int, ratio = ratio_k / ratio_den is the
     weight of the SOURCE amplitude (fundus.py:35,37; the reference draws ratio_k = randint(1, 10)).
     Returns clamp(RAM(src), clip) * scale + shift, float32 [B, C, H, W].
+
+    clean_out (optional, same shape as src): also receives the normalised clean batch src * scale + shift
+    (fundus.py:217-218), fused into the same kernel on the static shapes (ramdsir_mix_dual_f32).
 
     independent=True promises that this call neither reads nor overwrites anything the previous kernel on
     the stream produced (back-to-back batches with their own buffers); the launch may then overlap the tail
@@ -138,6 +142,10 @@ def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L
         _need_cuda_f32(out, "out", 4)
         if out.shape != src.shape or out.data_ptr() == src.data_ptr():
             raise ValueError("out must match src's shape and must not alias it")
+    if clean_out is not None:
+        _need_cuda_f32(clean_out, "clean_out", 4)
+        if clean_out.shape != src.shape or clean_out.data_ptr() in (src.data_ptr(), out.data_ptr()):
+            raise ValueError("clean_out must match src's shape and alias neither src nor out")
     pidx = _index_tensor(partner_idx, torch.int64, src.device, "partner_idx", 0, n_bank - 1)
     rk = _index_tensor(ratio_k, torch.int32, src.device, "ratio_k", 0, int(ratio_den))
     if pidx.numel() != bsz or rk.numel() != bsz:
@@ -145,8 +153,9 @@ def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L
     lib = _lib.load()
     with torch.cuda.device(src.device):
         ws, ws_ptr, ws_n = _workspace(workspace_bytes(bsz, c, h, w, b), src.device, workspace)
-        _lib.check(lib.ramdsir_mix_f32_ex(src.data_ptr(), bank.data_ptr(), pidx.data_ptr(), rk.data_ptr(),
-                                          out.data_ptr(), bsz, c, h, w, b, n_bank, int(ratio_den),
+        _lib.check(lib.ramdsir_mix_dual_f32(src.data_ptr(), bank.data_ptr(), pidx.data_ptr(), rk.data_ptr(),
+                                          out.data_ptr(), None if clean_out is None else clean_out.data_ptr(),
+                                          bsz, c, h, w, b, n_bank, int(ratio_den),
                                           float(clip[0]), float(clip[1]), float(scale), float(shift),
                                           ws_ptr, ws_n, _stream_ptr(stream),
                                           _lib.FLAG_INDEPENDENT if independent else 0))

@@ -106,11 +106,12 @@ __device__ __forceinline__ void prefetch_strip(const float4* x4, int strip, int 
   prefetch_l2(p + 8);
 }
 
-template <class CFG, bool BANK>
+template <class CFG, bool BANK, bool DUAL>
 __global__ void __launch_bounds__(CFG::nthreads, (CFG::smemBytes <= 113 * 1024) ? 2 : 1)
 ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__ bank,
                         const int64_t* __restrict__ pidx, const int32_t* __restrict__ rk, int ratio_den, int n_bank,
-                        int C, float* __restrict__ out, const Epilogue ep, const float* __restrict__ tables, int nplanes) {
+                        int C, float* __restrict__ out, const Epilogue ep, const float* __restrict__ tables, int nplanes,
+                        float* __restrict__ clean) {
   extern __shared__ __align__(16) unsigned char sm[];
   constexpr int NT = CFG::nthreads;
   const int tid = threadIdx.x;
@@ -171,7 +172,14 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
     {
       float4* y4 = reinterpret_cast<float4*>(out + plane * plane_px);
       auto ld_again = [&](size_t off) { return ldg_policy(x4 + off, pol_stream); };
-      auto st = [&](size_t off, float4 v) { stg_policy(y4 + off, v, pol_stream); };
+      // fused dual output: the normalised CLEAN image x * scale + shift (fundus.py:217-218) is
+      // written from the same read of x that feeds y = x + delta
+      float4* c4 = DUAL ? reinterpret_cast<float4*>(clean + plane * plane_px) : nullptr;
+      auto st = [&](size_t off, float4 v, float4 x) {
+        stg_policy(y4 + off, v, pol_stream);
+        if (DUAL) stg_policy(c4 + off, make_float4(fmaf(x.x, ep.scale, ep.shift), fmaf(x.y, ep.scale, ep.shift),
+                                                 fmaf(x.z, ep.scale, ep.shift), fmaf(x.w, ep.scale, ep.shift)), pol_stream);
+      };
       const int next = plane + gridDim.x;
       for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
         cf eva[8], evb[8], oda[8], odb[8];
@@ -314,6 +322,7 @@ using Cfg256 = SCfg<256, 256, 25>;
 using Cfg384 = SCfg<384, 384, 38>;
 using P256 = PCfg<256, 256, 25>;
 using P384 = PCfg<384, 384, 38>;
+thread_local float* t_clean = nullptr;   // fused dual output target of the calling thread's current call (or null)
 thread_local int t_overlap = 0;   // per-call flag of the calling thread (set by fused_mix, read by launch_static)
 std::atomic<int> g_variant{0};   // RAMDSIR_VARIANT_*: 0 auto (= float4 static kernels), 1 P2, 2 runtime-shape
 int static_id_of(int H, int W, int b, int variant) {
@@ -380,10 +389,13 @@ int launch(const FusedPlan& p, const float* src, const float* bank, const int64_
 
 template <class CFG, bool BANK>
 struct KernelOf {
-  static auto get() { return ram_fused_static_kernel<CFG, BANK>; }
+  static constexpr bool dual = true;    // takes the extra `clean` pointer; a second instantiation writes it
+  static auto get() { return ram_fused_static_kernel<CFG, BANK, false>; }
+  static auto get_dual() { return ram_fused_static_kernel<CFG, BANK, !BANK>; }
 };
 template <int H, int W, int B, bool BANK>
 struct KernelOf<PCfg<H, W, B>, BANK> {
+  static constexpr bool dual = false;
   static auto get() { return ram_fused_p2_kernel<PCfg<H, W, B>, BANK>; }
 };
 
@@ -391,9 +403,14 @@ template <class CFG, bool BANK>
 int launch_static(const FusedPlan& p, const float* src, const float* bank, const int64_t* pidx, const int32_t* rk,
                   int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
   auto kern = KernelOf<CFG, BANK>::get();
+  if constexpr (KernelOf<CFG, BANK>::dual) {
+    if (t_clean && !BANK) kern = KernelOf<CFG, BANK>::get_dual();
+  }
   static thread_local int per_sm = 0;  // per instantiation
   if (per_sm == 0) {
     RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
+    if constexpr (KernelOf<CFG, BANK>::dual)
+      RD_CUDA(cudaFuncSetAttribute(KernelOf<CFG, BANK>::get_dual(), cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
     RD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::nthreads, CFG::smemBytes));
     if (per_sm < 1) per_sm = 1;
   }
@@ -411,9 +428,15 @@ int launch_static(const FusedPlan& p, const float* src, const float* bank, const
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RD_CUDA(cudaLaunchKernelEx(&cfg, kern, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, (const float*)p.tables, nplanes));
+    if constexpr (KernelOf<CFG, BANK>::dual)
+      RD_CUDA(cudaLaunchKernelEx(&cfg, kern, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, (const float*)p.tables, nplanes, t_clean));
+    else
+      RD_CUDA(cudaLaunchKernelEx(&cfg, kern, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, (const float*)p.tables, nplanes));
   } else {
-    kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes);
+    if constexpr (KernelOf<CFG, BANK>::dual)
+      kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes, BANK ? nullptr : t_clean);
+    else
+      kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes);
   }
   count_launch();
   RD_CUDA(cudaGetLastError());
@@ -439,6 +462,11 @@ int dispatch(const FusedPlan& p, const float* src, const float* bank, const int6
 }
 }  // namespace
 
+bool fused_dual_supported(int H, int W, int b) {
+  const int id = static_id_of(H, W, b, g_variant.load(std::memory_order_relaxed));
+  return id == 1 || id == 2;
+}
+
 void fused_set_variant(int v) { g_variant.store(v, std::memory_order_relaxed); }
 
 bool fused_supported(int H, int W, int b) {
@@ -451,6 +479,7 @@ int fused_mix(const MixArgs& a, cudaStream_t st) {
   int rc = get_plan(a.H, a.W, a.b, &p);
   if (rc) return rc;
   t_overlap = a.independent ? 1 : 0;
+  t_clean = (p->static_id == 1 || p->static_id == 2) ? a.clean : nullptr;
   return dispatch<false>(*p, a.src, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, a.out, a.ep, a.B * a.C, st);
 }
 

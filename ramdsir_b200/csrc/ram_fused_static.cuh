@@ -214,6 +214,7 @@ RD_HD void s_inv_fft8(const unsigned char* sm, int t, int par, cf (&pa)[8], cf (
 // ---- inverse, second stage part 2: radix-2 combine of the two parities, add x, epilogue, store -----
 template <class CFG, int J>
 struct Combine {
+  // `st(off, y, x)`: y is the augmented pixel quad, x the source quad just read (for the fused dual output)
   template <class LoadF4, class StoreF4>
   static RD_HD void run(LoadF4 ld, StoreF4 st, Epilogue ep, size_t base, const cf (&eva)[8], const cf (&evb)[8],
                         const cf (&oda)[8], const cf (&odb)[8]) {
@@ -229,7 +230,7 @@ struct Combine {
       y.y = fmaf(fminf(fmaxf(x.y + bq.re, ep.lo), ep.hi), ep.scale, ep.shift);
       y.z = fmaf(fminf(fmaxf(x.z + a.im, ep.lo), ep.hi), ep.scale, ep.shift);
       y.w = fmaf(fminf(fmaxf(x.w + bq.im, ep.lo), ep.hi), ep.scale, ep.shift);
-      st(off, y);
+      st(off, y, x);
     }
     Combine<CFG, J + 1>::run(ld, st, ep, base, eva, evb, oda, odb);
   }

@@ -299,6 +299,28 @@ int run(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, s
 
 }  // namespace
 
+// y = x * scale + shift (the clean-image normalisation, fundus.py:217-218) for the paths without the fused dual output
+__global__ void g_affine(const float4* __restrict__ x, float4* __restrict__ y, size_t n4, float scale, float shift) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_float4(fmaf(v.x, scale, shift), fmaf(v.y, scale, shift), fmaf(v.z, scale, shift), fmaf(v.w, scale, shift));
+  }
+}
+
+__global__ void g_affine_scalar(const float* __restrict__ x, float* __restrict__ y, size_t n, float scale, float shift) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = fmaf(x[i], scale, shift);
+}
+
+int affine_f32(const float* x, float* y, size_t n, float scale, float shift, cudaStream_t st) {
+  if (n == 0) return RAMDSIR_OK;
+  const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0;
+  if (vec) g_affine<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n / 4, scale, shift);
+  else g_affine_scalar<<<148 * 8, 256, 0, st>>>(x, y, n, scale, shift);
+  count_launch(1);
+  RD_CUDA(cudaGetLastError());
+  return RAMDSIR_OK;
+}
+
 size_t full_amp_workspace_bytes(int N, int C, int H, int W) { return (size_t)N * C * H * (W / 2 + 1) * sizeof(float2); }
 
 int full_amp(const float* imgs, float* amp, int N, int C, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st) {

@@ -28,11 +28,14 @@ struct MixArgs {
   int B, C, H, W, b, n_bank, ratio_den;
   Epilogue ep;
   bool independent = false;   // RAMDSIR_FLAG_INDEPENDENT
+  float* clean = nullptr;     // fused dual output (static fused kernels only): x * scale + shift
 };
 
 // fused single-CTA-per-plane path (ram_fused.cu)
 bool fused_supported(int H, int W, int b);
 void fused_set_variant(int v);
+bool fused_dual_supported(int H, int W, int b);
+int affine_f32(const float* x, float* y, size_t n, float scale, float shift, cudaStream_t st);
 int fused_mix(const MixArgs& a, cudaStream_t st);
 int fused_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st);
 

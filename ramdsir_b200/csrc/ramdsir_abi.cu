@@ -129,6 +129,14 @@ int ramdsir_mix_f32_ex(const float* src_dev, const float* bank_dev, const int64_
                        const int32_t* ratio_k_dev, float* out_dev, int B, int C, int H, int W, int b,
                        int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
                        void* workspace_dev, size_t workspace_bytes, void* stream, unsigned flags) {
+  return ramdsir_mix_dual_f32(src_dev, bank_dev, partner_idx_dev, ratio_k_dev, out_dev, nullptr, B, C, H, W, b, n_bank,
+                              ratio_den, clip_lo, clip_hi, scale, shift, workspace_dev, workspace_bytes, stream, flags);
+}
+
+int ramdsir_mix_dual_f32(const float* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
+                         const int32_t* ratio_k_dev, float* out_dev, float* clean_out_dev, int B, int C, int H, int W,
+                         int b, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
+                         void* workspace_dev, size_t workspace_bytes, void* stream, unsigned flags) {
   int rc = check_shape(B, C, H, W, b);
   if (rc) return rc;
   if (B == 0) return RAMDSIR_OK;
@@ -148,6 +156,18 @@ int ramdsir_mix_f32_ex(const float* src_dev, const float* bank_dev, const int64_
             Epilogue{clip_lo, clip_hi, scale, shift}};
   a.independent = (flags & RAMDSIR_FLAG_INDEPENDENT) != 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (clean_out_dev) {
+    if (!aligned16(clean_out_dev) || clean_out_dev == out_dev || clean_out_dev == src_dev) {
+      set_error("mix_dual: clean_out must be 16-byte aligned and distinct from src and out");
+      return RAMDSIR_ERR_INVALID;
+    }
+    if (path_of(H, W, b) == RAMDSIR_PATH_FUSED && fused_dual_supported(H, W, b)) {
+      a.clean = clean_out_dev;      // written by the RAM kernel itself, from the same read of src
+    } else {
+      rc = affine_f32(src_dev, clean_out_dev, (size_t)B * C * H * W, scale, shift, st);
+      if (rc) return rc;
+    }
+  }
   switch (path_of(H, W, b)) {
     case RAMDSIR_PATH_FUSED: return fused_mix(a, st);
     case RAMDSIR_PATH_MULTIPASS: return multipass_mix(a, workspace_dev, workspace_bytes, st);

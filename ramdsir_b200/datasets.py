@@ -196,7 +196,10 @@ class RamBatchHook:
         bank = build_amp_bank(partner, L=self.L)                 # row i is sample i's partner
         idx = torch.arange(img_raw.shape[0], device=self.device)
         lo, hi, scale, shift = FUNDUS_EPILOGUE if self.dataset == "fundus" else PROSTATE_EPILOGUE
+        # fundus: the kernel also emits the normalised clean batch from the same read of img_raw (fused dual output)
+        img = torch.empty_like(img_raw) if self.dataset == "fundus" else None
         img_freq = ram_mix_batch(img_raw, bank, idx, torch.as_tensor(ratio_k, dtype=torch.int32), L=self.L,
-                                 clip=(lo, hi), scale=scale, shift=shift)
-        img = img_raw / 127.5 - 1.0 if self.dataset == "fundus" else img_raw
+                                 clip=(lo, hi), scale=scale, shift=shift, clean_out=img)
+        if img is None:
+            img = img_raw                                         # prostate.py:190-193: the clean image is untouched
         return img, img_freq, mask.to(self.device, non_blocking=True)

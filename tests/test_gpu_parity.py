@@ -374,6 +374,29 @@ def test_hires_1024(R):
     _amp_identity(R, 24, 3, 1024, 1024, 5, 1339)            # BASELINE config 5 shape, spans several L2 chunks
 
 
+@pytest.mark.parametrize("shape", [(3, 256, 256), (1, 384, 384), (2, 64, 128), (1, 33, 45), (1, 512, 512)],
+                         ids=["static256", "static384", "runtime", "generic", "multipass"])
+def test_dual_output(R, shape):
+    """ramdsir_mix_dual_f32: img_freq identical to the single-output call, clean = src * scale + shift
+    (fundus.py:217-218 to 1 ulp), on every kernel path."""
+    c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    src = torch.randint(0, 256, (6, c, h, w), device="cuda", generator=g).float()
+    bank = R.build_amp_bank(torch.randint(0, 256, (3, c, h, w), device="cuda", generator=g).float())
+    pidx, rk = [0, 1, 2, 0, 1, 2], [1, 3, 5, 7, 9, 10]
+    kw = dict(clip=(0.0, 255.0), scale=1 / 127.5, shift=-1.0)
+    single = R.ram_mix_batch(src, bank, pidx, rk, **kw)
+    clean = torch.empty_like(src)
+    dual = R.ram_mix_batch(src, bank, pidx, rk, clean_out=clean, **kw)
+    assert torch.equal(single, dual)
+    want = src.cpu().numpy().copy()
+    want /= 127.5
+    want -= 1.0
+    assert np.abs(clean.cpu().numpy() - want).max() <= 1.2e-7          # 1 ulp at |v| <= 1
+    with pytest.raises(ValueError):
+        R.ram_mix_batch(src, bank, pidx, rk, clean_out=src, **kw)
+
+
 def test_host_pipeline_matches_device_path(R):
     """ramdsir_mix_host_f32 (pinned host buffers, chunked H2D/compute/D2H) == ram_mix_batch bit for bit."""
     from ramdsir_b200.host import HostPipeline
