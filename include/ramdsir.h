@@ -69,7 +69,9 @@ int ramdsir_path(int C, int H, int W, int b);
 int ramdsir_force_path(int path);
 
 /* Tuning/testing knob for the fused path: 0 = auto (float4 static-shape kernels where instantiated),
- * 1 = "P2" static kernels (one packed column per thread, 64 registers), 2 = runtime-shape kernel. */
+ * 1 = "P2" static kernels (one packed column per thread, 64 registers), 2 = runtime-shape kernel,
+ * 4 = "x2" static kernels (packed f32x2 arithmetic).  All variants compute the same result within tolerance;
+ * 0 is the fastest measured. */
 int ramdsir_set_fused_variant(int variant);
 
 /* Scratch bytes needed to process `n_images` images of this shape in one call (0 for the fused path). */

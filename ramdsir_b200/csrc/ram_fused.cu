@@ -201,6 +201,105 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// x2 kernel (ram_fused_x2.cuh): the static float4 pipeline with packed f32x2 arithmetic (FADD2 / FMUL2 / FFMA2).
+template <class CFG, bool BANK, bool DUAL>
+__global__ void __launch_bounds__(CFG::nthreads, (CFG::smemBytes <= 113 * 1024) ? 2 : 1)
+ram_fused_x2_kernel(const float* __restrict__ src, const float* __restrict__ bank, const int64_t* __restrict__ pidx,
+                    const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ out,
+                    const Epilogue ep, const float* __restrict__ tables, int nplanes, float* __restrict__ clean) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  constexpr int NT = CFG::nthreads;
+  const int tid = threadIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;");
+  unsigned long long pol_keep, pol_stream;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  {
+    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
+    const float4* g = reinterpret_cast<const float4*>(tables);
+    for (int i = tid; i < CFG::tabBytes / 16; i += NT) tab[i] = g[i];
+  }
+  __syncthreads();
+  constexpr size_t plane_px = (size_t)CFG::H * CFG::W;
+  constexpr size_t patch_px = (size_t)CFG::nb * CFG::nb;
+  const bool worker = tid < 2 * CFG::ntask;      // exchange-stage tasks: 2 parities x 128
+  const int par2 = tid >> 7, u = tid & 127;
+  for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
+    const float4* x4 = reinterpret_cast<const float4*>(src + plane * plane_px);
+    auto ld_first = [&](size_t off) { return BANK ? __ldg(x4 + off) : ldg_policy(x4 + off, pol_keep); };
+    for (int strip = 0; strip < CFG::nstrips; ++strip) {
+      cf2 v[16];
+      x_f1_load_fft_tw<CFG>(ld_first, sm, strip, tid, v);
+      if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        x_f1_store_half<CFG>(sm, tid, half, v);
+        __syncthreads();
+        if (worker) {
+          if (par2 == 0) x_f1_pruned<CFG, 0>(sm, strip, half, u);
+          else x_f1_pruned<CFG, 1>(sm, strip, half, u);
+        }
+        __syncthreads();
+      }
+    }
+    Epilogue epp = ep;
+    float omr = 0.f;
+    if (!BANK) {
+      const int img = plane / C, ch = plane - img * C;
+      const long long p = pidx[img];
+      const bool ok = (p >= 0 && p < (long long)n_bank);
+      if (!ok) epp.scale = __int_as_float(0x7fc00000);
+      omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
+      const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
+      for (int i = tid; i < (int)patch_px; i += NT) s_stage_patch<CFG>(sm, patch, i);
+    }
+    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) x_row_fwd<CFG>(sm, r);
+    __syncthreads();
+    if (BANK) {
+      float* po = out + plane * patch_px;
+      for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) x_band_amp<CFG>(sm, po, q);
+      __syncthreads();
+      continue;
+    }
+    for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) x_band_mix<CFG>(sm, omr, q);
+    __syncthreads();
+    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) x_row_inv<CFG>(sm, r);
+    __syncthreads();
+    {
+      float4* y4 = reinterpret_cast<float4*>(out + plane * plane_px);
+      auto ld_again = [&](size_t off) { return ldg_policy(x4 + off, pol_stream); };
+      float4* c4 = DUAL ? reinterpret_cast<float4*>(clean + plane * plane_px) : nullptr;
+      auto st = [&](size_t off, float4 v, float4 x) {
+        stg_policy(y4 + off, v, pol_stream);
+        if (DUAL) stg_policy(c4 + off, make_float4(fmaf(x.x, ep.scale, ep.shift), fmaf(x.y, ep.scale, ep.shift),
+                                                   fmaf(x.z, ep.scale, ep.shift), fmaf(x.w, ep.scale, ep.shift)), pol_stream);
+      };
+      const int next = plane + gridDim.x;
+      for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
+        cf2 ev[8], od[8];
+        if (strip > 0) prefetch_strip<CFG>(x4, strip - 1, tid);
+        else if (next < nplanes) prefetch_strip<CFG>(reinterpret_cast<const float4*>(src + next * plane_px), 0, tid);
+        if (worker) {
+          if (par2 == 0) x_inv_pruned<CFG, 0>(sm, strip, 0, u);
+          else x_inv_pruned<CFG, 1>(sm, strip, 0, u);
+        }
+        __syncthreads();
+        x_inv_fft8<CFG>(sm, tid, 0, ev);
+        __syncthreads();
+        if (worker) {
+          if (par2 == 0) x_inv_pruned<CFG, 0>(sm, strip, 1, u);
+          else x_inv_pruned<CFG, 1>(sm, strip, 1, u);
+        }
+        __syncthreads();
+        x_inv_fft8<CFG>(sm, tid, 1, od);
+        __syncthreads();
+        x_inv_combine_store<CFG>(ld_again, st, epp, strip, tid, ev, od);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // P2 kernel (ram_fused_p2.cuh): one packed complex column per thread, 64 registers, 1024 threads/SM.
 __device__ __forceinline__ float2 ldg_policy2(const float2* p, unsigned long long pol) {
   float2 v;
@@ -322,11 +421,18 @@ using Cfg256 = SCfg<256, 256, 25>;
 using Cfg384 = SCfg<384, 384, 38>;
 using P256 = PCfg<256, 256, 25>;
 using P384 = PCfg<384, 384, 38>;
+using X256 = XCfg<256, 256, 25>;
+using X384 = XCfg<384, 384, 38>;
 thread_local float* t_clean = nullptr;   // fused dual output target of the calling thread's current call (or null)
 thread_local int t_overlap = 0;   // per-call flag of the calling thread (set by fused_mix, read by launch_static)
 std::atomic<int> g_variant{0};   // RAMDSIR_VARIANT_*: 0 auto (= float4 static kernels), 1 P2, 2 runtime-shape
 int static_id_of(int H, int W, int b, int variant) {
   if (variant == 2) return 0;
+  if (variant == 4) {
+    if (H == 256 && W == 256 && b == 25) return 7;
+    if (H == 384 && W == 384 && b == 38) return 8;
+    return 0;
+  }
   const int base = (variant == 1) ? 2 : 0;
   if (H == 256 && W == 256 && b == 25) return base + 1;
   if (H == 384 && W == 384 && b == 38) return base + 2;
@@ -350,12 +456,15 @@ int get_plan(int H, int W, int b, FusedPlan** out) {
     }
     p.static_id = static_id_of(H, W, b, variant);
     const int tab_bytes = p.static_id == 1 ? Cfg256::tabBytes : p.static_id == 2 ? Cfg384::tabBytes
-                        : p.static_id == 3 ? P256::tabBytes : p.static_id == 4 ? P384::tabBytes : p.S.tabBytes;
+                        : p.static_id == 3 ? P256::tabBytes : p.static_id == 4 ? P384::tabBytes
+                        : p.static_id == 7 ? X256::tabBytes : p.static_id == 8 ? X384::tabBytes : p.S.tabBytes;
     std::vector<float> host(tab_bytes / 4);
     if (p.static_id == 1) fused_tables_fill_static<Cfg256>(host.data());
     else if (p.static_id == 2) fused_tables_fill_static<Cfg384>(host.data());
     else if (p.static_id == 3) fused_tables_fill_p2<P256>(host.data());
     else if (p.static_id == 4) fused_tables_fill_p2<P384>(host.data());
+    else if (p.static_id == 7) fused_tables_fill_x2<X256>(host.data());
+    else if (p.static_id == 8) fused_tables_fill_x2<X384>(host.data());
     else fused_tables_fill(p.S, host.data());
     RD_CUDA(cudaMalloc(&p.tables, tab_bytes));
     RD_CUDA(cudaMemcpy(p.tables, host.data(), tab_bytes, cudaMemcpyHostToDevice));
@@ -397,6 +506,13 @@ template <int H, int W, int B, bool BANK>
 struct KernelOf<PCfg<H, W, B>, BANK> {
   static constexpr bool dual = false;
   static auto get() { return ram_fused_p2_kernel<PCfg<H, W, B>, BANK>; }
+};
+
+template <int H, int W, int B, bool BANK>
+struct KernelOf<XCfg<H, W, B>, BANK> {
+  static constexpr bool dual = true;
+  static auto get() { return ram_fused_x2_kernel<XCfg<H, W, B>, BANK, false>; }
+  static auto get_dual() { return ram_fused_x2_kernel<XCfg<H, W, B>, BANK, !BANK>; }
 };
 
 template <class CFG, bool BANK>
@@ -450,6 +566,8 @@ int dispatch(const FusedPlan& p, const float* src, const float* bank, const int6
   if (p.static_id == 2) return launch_static<Cfg384, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
   if (p.static_id == 3) return launch_static<P256, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
   if (p.static_id == 4) return launch_static<P384, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
+  if (p.static_id == 7) return launch_static<X256, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
+  if (p.static_id == 8) return launch_static<X384, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
   switch (p.S.MM) {
     case 0:
     case 1: return launch<1, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
@@ -464,7 +582,7 @@ int dispatch(const FusedPlan& p, const float* src, const float* bank, const int6
 
 bool fused_dual_supported(int H, int W, int b) {
   const int id = static_id_of(H, W, b, g_variant.load(std::memory_order_relaxed));
-  return id == 1 || id == 2;
+  return id == 1 || id == 2 || id == 7 || id == 8;
 }
 
 void fused_set_variant(int v) { g_variant.store(v, std::memory_order_relaxed); }
@@ -479,7 +597,7 @@ int fused_mix(const MixArgs& a, cudaStream_t st) {
   int rc = get_plan(a.H, a.W, a.b, &p);
   if (rc) return rc;
   t_overlap = a.independent ? 1 : 0;
-  t_clean = (p->static_id == 1 || p->static_id == 2) ? a.clean : nullptr;
+  t_clean = (p->static_id == 1 || p->static_id == 2 || p->static_id == 7 || p->static_id == 8) ? a.clean : nullptr;
   return dispatch<false>(*p, a.src, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, a.out, a.ep, a.B * a.C, st);
 }
 

@@ -76,8 +76,8 @@ int ramdsir_force_path(int path) {
 }
 
 int ramdsir_set_fused_variant(int variant) {
-  if (variant < 0 || variant > 2) {
-    set_error("set_fused_variant: 0 (auto), 1 (P2: one packed column per thread) or 2 (runtime-shape kernel)");
+  if (variant < 0 || variant > 4 || variant == 3) {
+    set_error("set_fused_variant: 0 (auto), 1 (P2: one packed column per thread), 2 (runtime-shape kernel), 4 (x2: packed f32x2 arithmetic)");
     return RAMDSIR_ERR_INVALID;
   }
   fused_set_variant(variant);

@@ -188,7 +188,7 @@ def test_constant_planes_take_phase_zero_like_the_reference(R, shape):
     check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "constant planes")
 
 
-@pytest.mark.parametrize("variant", [1, 2], ids=["p2", "runtime"])
+@pytest.mark.parametrize("variant", [1, 2, 4], ids=["p2", "runtime", "x2"])
 @pytest.mark.parametrize("shape", [(3, 256, 256, True), (1, 384, 384, False)], ids=["fundus", "prostate"])
 def test_alternative_fused_variants(R, variant, shape):
     """The other two implementations of the fused pipeline (selected through ramdsir_set_fused_variant)
