@@ -80,7 +80,21 @@ ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank, const int
   auto live = [&](int r) { return !((r & 1) && kh0 + (r >> 1) == 0); };
   for (int i = tid; i < ng * 2 * M; i += NT) {
     const int r = i / M, m = i % M;
-    if (live(r)) R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + m] = zrow(r)[m];
+    if (live(r)) R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)] = zrow(r)[m];
+  }
+  // stage the partner-patch rows b + kh and b - kh of every kh handled here (coalesced; consumed by the band tasks)
+  float omr = 0.f;
+  if (!BANK) {
+    const int img = plane / C, ch = plane - img * C;
+    const long long p = pidx[img];
+    const bool ok = (p >= 0 && p < (long long)n_bank);
+    omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
+    const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * ((size_t)CFG::nb * CFG::nb);
+    float* P = reinterpret_cast<float*>(sm + CFG::bOffP);
+    for (int i = tid; i < ng * 2 * CFG::nb; i += NT) {
+      const int r = i / CFG::nb, j = i % CFG::nb, kh = kh0 + (r >> 1);
+      P[i] = patch[(size_t)(CFG::b + ((r & 1) ? -kh : kh)) * CFG::nb + j];
+    }
   }
   __syncthreads();
   for (int t = tid; t < ng * 2 * CFG::N1w; t += NT) {
@@ -104,14 +118,10 @@ ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank, const int
     return;
   }
   {
-    const int img = plane / C, ch = plane - img * C;
-    const long long p = pidx[img];
-    const bool ok = (p >= 0 && p < (long long)n_bank);
-    const float omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
-    const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
+    const float* P = reinterpret_cast<const float*>(sm + CFG::bOffP);
     for (int t = tid; t < ng * nband; t += NT) {
       const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
-      if (live(2 * g + srow)) m_band<CFG, false>(R + (size_t)g * RP, D + g * DP, tab, patch, nullptr, omr, kh0 + g, srow, tt % (CFG::b + 1));
+      if (live(2 * g + srow)) m_band<CFG, false>(R + (size_t)g * RP, D + g * DP, tab, P + g * 2 * CFG::nb, nullptr, omr, kh0 + g, srow, tt % (CFG::b + 1));
     }
   }
   __syncthreads();
@@ -132,7 +142,7 @@ ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank, const int
   __syncthreads();
   for (int i = tid; i < ng * 2 * M; i += NT) {
     const int r = i / M, m = i % M;
-    if (live(r)) zrow(r)[m] = R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + m];
+    if (live(r)) zrow(r)[m] = R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)];
   }
 }
 

@@ -41,10 +41,12 @@ struct KCfg {
   // pass B shared memory: KG pairs of rows (+kh, -kh) of M float4 (+1 pad), their D rows, tables
   static constexpr int KG = 4;                                 // kh values per CTA
   static constexpr int nkg = (B_ + 1 + KG - 1) / KG;           // CTAs per plane
-  static constexpr int rowPitch = M + 1;
+  static constexpr int SP = N1w + 1;                           // padded pitch of a k2 / j group inside a row: conflict-free
+  static constexpr int rowPitch = 16 * SP;                     // float4 per staged row (element c1 + N1w j lives at c1 + SP j)
   static constexpr int bOffR = 0;                              // [KG][2][rowPitch] float4
   static constexpr int bOffD = s_al16(KG * 2 * rowPitch * 16); // [KG][2][b+1] float2
-  static constexpr int bOffTab = bOffD + s_al16(KG * 2 * (B_ + 1) * 8);
+  static constexpr int bOffP = bOffD + s_al16(KG * 2 * (B_ + 1) * 8);   // [KG][2][nb] float: partner patch rows b+kh, b-kh
+  static constexpr int bOffTab = bOffP + s_al16(KG * 2 * nb * 4);
   static constexpr int tTWM = 0;                               // [N1w][16] float2  W_M^(c1 k2)
   static constexpr int tTW3 = tTWM + N1w * 16 * 2;             // [3][b+1] float2   W_W^(g kw)
   static constexpr int tQ = ((tTW3 + 3 * (B_ + 1) * 2) + 3) & ~3;   // [nb] float4: (Qa, Qb)[kw]
@@ -200,7 +202,7 @@ RD_HD void m_row_stage1(float4* Rbase, const float* tab, int task) {
   cf va[16], vb[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const float4 q = R[CFG::N1w * j];
+    const float4 q = R[CFG::SP * j];
     va[j] = cf{q.x, q.y};
     vb[j] = cf{q.z, q.w};
     if (DIR > 0) {   // inverse: undo the twiddle first (input index is k2)
@@ -219,7 +221,7 @@ RD_HD void m_row_stage1(float4* Rbase, const float* tab, int task) {
       a = cmul(a, cf{w.x, w.y});
       bq = cmul(bq, cf{w.x, w.y});
     }
-    R[CFG::N1w * k] = make_float4(a.re, a.im, bq.re, bq.im);
+    R[CFG::SP * k] = make_float4(a.re, a.im, bq.re, bq.im);
   }
 }
 
@@ -227,7 +229,7 @@ RD_HD void m_row_stage1(float4* Rbase, const float* tab, int task) {
 template <class CFG, int DIR>
 RD_HD void m_row_stage2(float4* Rbase, int task) {
   const int row = task / 16, k2 = task % 16;
-  float4* R = Rbase + (size_t)row * CFG::rowPitch + CFG::N1w * k2;
+  float4* R = Rbase + (size_t)row * CFG::rowPitch + CFG::SP * k2;
   cf va[CFG::N1w], vb[CFG::N1w];
 #pragma unroll
   for (int i = 0; i < CFG::N1w; ++i) {
@@ -248,7 +250,7 @@ RD_HD void m_row_stage2(float4* Rbase, int task) {
 template <class CFG>
 RD_HD int m_slot(int kw) {
   const int k = (kw + CFG::M) % CFG::M;
-  return CFG::N1w * (k & 15) + (k >> 4);
+  return CFG::SP * (k & 15) + (k >> 4);
 }
 
 // Band task: bin (s kh, kw), kw in [0, b], s = +1 (row 0 = +kh) or -1 (row 1 = -kh).  Writes D[s][kw].
@@ -276,7 +278,8 @@ RD_HD void m_band(const float4* R, float2* D, const float* tab, const float* pat
     patch_out[(size_t)(CFG::nb - 1 - khi) * CFG::nb + (CFG::b - kw)] = a;
     return;
   }
-  const float at = 0.5f * (patch[(size_t)khi * CFG::nb + (kw + CFG::b)] + patch[(size_t)(CFG::nb - 1 - khi) * CFG::nb + (CFG::b - kw)]);
+  // `patch` points at the two staged rows of this kh pair: [0] = row b + kh, [1] = row b - kh (shared memory)
+  const float at = 0.5f * (patch[srow * CFG::nb + (kw + CFG::b)] + patch[(kh == 0 ? 0 : 1 - srow) * CFG::nb + (CFG::b - kw)]);
   cf d;
   if (a2 > 0.f) {
     const float s = one_minus_ratio * (at / sqrtf(a2) - 1.0f) * CFG::invHW;
@@ -305,7 +308,7 @@ RD_HD void m_fill_v(float4* R, const float2* D, const float* tab, int kh, int sr
     const cf a = cmul(d, cf{qq.x, qq.y}), bq = cmul(d, cf{qq.z, qq.w});
     v = make_float4(a.re, a.im, bq.re, bq.im);
   }
-  R[(size_t)srow * CFG::rowPitch + slot_idx] = v;
+  R[(size_t)srow * CFG::rowPitch + CFG::SP * k2 + q] = v;
 }
 
 }  // namespace ramdsir

@@ -324,7 +324,7 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
         const float* tab = reinterpret_cast<const float*>(smb.data() + CFG::bOffTab);
         const int rows[2] = {CFG::b + kh, CFG::b - kh};
         for (int r = 0; r < nrows; ++r)
-          for (int m = 0; m < CFG::M; ++m) R[r * CFG::rowPitch + m] = Zg[(size_t)rows[r] * CFG::M + m];
+          for (int m = 0; m < CFG::M; ++m) R[r * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)] = Zg[(size_t)rows[r] * CFG::M + m];
         for (int t = 0; t < nrows * CFG::N1w; ++t) m_row_stage1<CFG, -1>(R, tab, t);
         for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, -1>(R, t);
         if (bank_out) {
@@ -332,13 +332,18 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
             m_band<CFG, true>(R, D, tab, nullptr, bank_out + pl * psz, 0.f, kh, t / (CFG::b + 1), t % (CFG::b + 1));
           continue;
         }
+        std::vector<float> prow(2 * CFG::nb);
+        for (int j = 0; j < CFG::nb; ++j) {
+          prow[j] = patch[(size_t)(CFG::b + kh) * CFG::nb + j];
+          prow[CFG::nb + j] = patch[(size_t)(CFG::b - kh) * CFG::nb + j];
+        }
         for (int t = 0; t < nrows * (CFG::b + 1); ++t)
-          m_band<CFG, false>(R, D, tab, patch, nullptr, omr, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+          m_band<CFG, false>(R, D, tab, prow.data(), nullptr, omr, kh, t / (CFG::b + 1), t % (CFG::b + 1));
         for (int t = 0; t < nrows * CFG::M; ++t) m_fill_v<CFG>(R, D, tab, kh, t / CFG::M, t % CFG::M);
         for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, 1>(R, t);
         for (int t = 0; t < nrows * CFG::N1w; ++t) m_row_stage1<CFG, 1>(R, tab, t);
         for (int r = 0; r < nrows; ++r)
-          for (int m = 0; m < CFG::M; ++m) Zg[(size_t)rows[r] * CFG::M + m] = R[r * CFG::rowPitch + m];
+          for (int m = 0; m < CFG::M; ++m) Zg[(size_t)rows[r] * CFG::M + m] = R[r * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)];
       }
       if (bank_out) continue;
       // pass C
