@@ -7,7 +7,7 @@
 #include "ram_multipass_host.h"
 
 #ifndef RAMDSIR_MP_CHUNK_MB
-#define RAMDSIR_MP_CHUNK_MB 90   // x + band workspace of one chunk of planes (measured: 18-plane chunks beat 9-plane chunks, 56k vs 42k img/s)
+#define RAMDSIR_MP_CHUNK_MB 1024   // planes per pass = this budget / (x + band workspace per plane). Measured on B200 (64x3x1024^2): 9-plane chunks 42k img/s, 18: 64.6k, 36: 66.9k -- L2 does not retain 4 MB planes between passes, so fewer, larger launches win
 #endif
 
 namespace ramdsir {
