@@ -342,6 +342,17 @@ def run_ours(args, rank, local_rank, world):
         for _ in range(e2e_steps):
             pipe.mix(src_h, bank, pidx_h, rk_h, out_h, epilogue=epi)
         e2e_s = time.perf_counter() - t0
+        # same leg with uint8 host images (what a fundus loader holds, fundus.py:212): H2D bytes / 4
+        e2e_u8 = None
+        if EPI_NAME == "fundus":
+            src_u8 = src_h.to(torch.uint8).pin_memory()
+            for _ in range(2):
+                pipe.mix(src_u8, bank, pidx_h, rk_h, out_h, epilogue=epi)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                pipe.mix(src_u8, bank, pidx_h, rk_h, out_h, epilogue=epi)
+            e2e_u8 = BATCH * e2e_steps / (time.perf_counter() - t0)
     same = bool(torch.equal(out_h, outs[0].cpu())) and bool(torch.equal(outs[0], outs[1]))
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -378,7 +389,9 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "images/s",
                     "h2d_bytes_per_step": int(src_h.numel() * 4 + pidx_h.nbytes + rk_h.nbytes),
                     "d2h_bytes_per_step": int(out_h.numel() * 4), "steps": e2e_steps,
-                    "matches_device_path": same, "timing": "wall clock around the blocking C-ABI call"},
+                    "matches_device_path": same, "timing": "wall clock around the blocking C-ABI call",
+                    "uint8_input_value": e2e_u8,
+                    "uint8_input_note": "rank 0, same call with uint8 host images (ramdsir_mix_host_u8): H2D bytes / 4"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -140,6 +140,12 @@ int ramdsir_mix_host_f32(ramdsir_pipe_t* pipe, const float* src_host, const floa
                          const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host,
                          int B, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale,
                          float shift);
+/* Same with a uint8 source batch [B, C, H, W] (what a fundus loader holds before astype(float32), fundus.py:212):
+ * a quarter of the host->device bytes; widened to float32 on the device.  Output is float32 as before. */
+int ramdsir_mix_host_u8(ramdsir_pipe_t* pipe, const unsigned char* src_host, const float* bank_dev,
+                        const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host,
+                        int B, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale,
+                        float shift);
 /* number of kernel launches the library has issued on this process so far (bench bookkeeping) */
 uint64_t ramdsir_launch_count(void);
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ramdsir_version", "ramdsir_last_error", "ramdsir_band_halfwidth", "ramdsir_path", "ramdsir_force_path", "ramdsir_set_fused_variant",
     "ramdsir_workspace_bytes", "ramdsir_bank_build_f32", "ramdsir_mix_f32", "ramdsir_mix_f32_ex", "ramdsir_mix_dual_f32",
     "ramdsir_amp_spectrum_workspace_bytes", "ramdsir_amp_spectrum_f32", "ramdsir_band_blend_f32",
-    "ramdsir_pipe_create", "ramdsir_pipe_destroy", "ramdsir_mix_host_f32", "ramdsir_launch_count",
+    "ramdsir_pipe_create", "ramdsir_pipe_destroy", "ramdsir_mix_host_f32", "ramdsir_mix_host_u8", "ramdsir_launch_count",
 ]
 
 
@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
             return LIB_PATH
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-cudart", "shared", "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
+           "-t", "4", "-cudart", "shared", "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
            "-o", LIB_PATH] + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
@@ -82,6 +82,7 @@ def _declare(lib):
     lib.ramdsir_pipe_destroy.argtypes = [vp]
     lib.ramdsir_pipe_destroy.restype = None
     lib.ramdsir_mix_host_f32.argtypes = [vp] * 6 + [c.c_int] * 3 + [c.c_float] * 4
+    lib.ramdsir_mix_host_u8.argtypes = [vp] * 6 + [c.c_int] * 3 + [c.c_float] * 4
     lib.ramdsir_launch_count.restype = c.c_uint64
     return lib
 

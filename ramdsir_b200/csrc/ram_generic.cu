@@ -321,6 +321,26 @@ int affine_f32(const float* x, float* y, size_t n, float scale, float shift, cud
   return RAMDSIR_OK;
 }
 
+// uint8 -> float32 widening for the host pipeline's uint8 ingestion (fundus loaders hold uint8 images, fundus.py:212)
+__global__ void g_u8_to_f32(const uchar4* __restrict__ x, float4* __restrict__ y, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const uchar4 v = x[i];
+    y[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+  }
+}
+
+int u8_to_f32(const unsigned char* x, float* y, size_t n, cudaStream_t st) {
+  if (n == 0) return RAMDSIR_OK;
+  if (n % 4 || (reinterpret_cast<uintptr_t>(x) & 3u) || (reinterpret_cast<uintptr_t>(y) & 15u)) {
+    set_error("u8_to_f32: size must be a multiple of 4 and the buffers aligned");
+    return RAMDSIR_ERR_INVALID;
+  }
+  g_u8_to_f32<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const uchar4*>(x), reinterpret_cast<float4*>(y), n / 4);
+  count_launch(1);
+  RD_CUDA(cudaGetLastError());
+  return RAMDSIR_OK;
+}
+
 size_t full_amp_workspace_bytes(int N, int C, int H, int W) { return (size_t)N * C * H * (W / 2 + 1) * sizeof(float2); }
 
 int full_amp(const float* imgs, float* amp, int N, int C, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st) {

@@ -35,6 +35,7 @@ struct MixArgs {
 bool fused_supported(int H, int W, int b);
 void fused_set_variant(int v);
 bool fused_dual_supported(int H, int W, int b);
+int u8_to_f32(const unsigned char* x, float* y, size_t n, cudaStream_t st);
 int affine_f32(const float* x, float* y, size_t n, float scale, float shift, cudaStream_t st);
 int fused_mix(const MixArgs& a, cudaStream_t st);
 int fused_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st);

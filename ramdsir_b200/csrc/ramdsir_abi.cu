@@ -211,6 +211,7 @@ struct ramdsir_pipe {
   size_t img_elems, ws_bytes;
   cudaStream_t st[NSLOT];
   float* d_src[NSLOT];
+  unsigned char* d_u8[NSLOT];   // staging for uint8 ingestion (allocated on first use)
   float* d_out[NSLOT];
   int64_t* d_pidx[NSLOT];
   int32_t* d_rk[NSLOT];
@@ -253,16 +254,34 @@ void ramdsir_pipe_destroy(ramdsir_pipe_t* p) {
   if (!p) return;
   for (int i = 0; i < ramdsir_pipe::NSLOT; ++i) {
     if (p->st[i]) { cudaStreamSynchronize(p->st[i]); cudaStreamDestroy(p->st[i]); }
-    cudaFree(p->d_src[i]); cudaFree(p->d_out[i]); cudaFree(p->d_pidx[i]); cudaFree(p->d_rk[i]); cudaFree(p->d_ws[i]);
+    cudaFree(p->d_src[i]); cudaFree(p->d_u8[i]); cudaFree(p->d_out[i]); cudaFree(p->d_pidx[i]); cudaFree(p->d_rk[i]); cudaFree(p->d_ws[i]);
   }
   delete p;
 }
+
+static int mix_host_impl(ramdsir_pipe_t* p, const float* src_host, const unsigned char* src_u8_host, const float* bank_dev,
+                         const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host, int B,
+                         int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift);
 
 int ramdsir_mix_host_f32(ramdsir_pipe_t* p, const float* src_host, const float* bank_dev,
                          const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host,
                          int B, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale,
                          float shift) {
-  if (!p || !src_host || !bank_dev || !partner_idx_host || !ratio_k_host || !out_host || B < 0) {
+  return mix_host_impl(p, src_host, nullptr, bank_dev, partner_idx_host, ratio_k_host, out_host, B, n_bank, ratio_den,
+                       clip_lo, clip_hi, scale, shift);
+}
+
+int ramdsir_mix_host_u8(ramdsir_pipe_t* p, const unsigned char* src_host, const float* bank_dev,
+                        const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host,
+                        int B, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift) {
+  return mix_host_impl(p, nullptr, src_host, bank_dev, partner_idx_host, ratio_k_host, out_host, B, n_bank, ratio_den,
+                       clip_lo, clip_hi, scale, shift);
+}
+
+static int mix_host_impl(ramdsir_pipe_t* p, const float* src_host, const unsigned char* src_u8_host, const float* bank_dev,
+                         const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host, int B,
+                         int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift) {
+  if (!p || (!src_host && !src_u8_host) || !bank_dev || !partner_idx_host || !ratio_k_host || !out_host || B < 0) {
     set_error("mix_host: invalid arguments");
     return RAMDSIR_ERR_INVALID;
   }
@@ -276,7 +295,14 @@ int ramdsir_mix_host_f32(ramdsir_pipe_t* p, const float* src_host, const float* 
     const int n = (B - i0 < p->chunk) ? B - i0 : p->chunk;
     cudaStream_t st = p->st[slot];
     const size_t off = (size_t)i0 * p->img_elems, bytes = (size_t)n * p->img_elems * sizeof(float);
-    RD_CUDA(cudaMemcpyAsync(p->d_src[slot], src_host + off, bytes, cudaMemcpyHostToDevice, st));
+    if (src_u8_host) {   // uint8 ingestion: a quarter of the H2D bytes, widened on the device
+      if (!p->d_u8[slot]) RD_CUDA(cudaMalloc(&p->d_u8[slot], p->img_elems * (size_t)p->chunk));
+      RD_CUDA(cudaMemcpyAsync(p->d_u8[slot], src_u8_host + off, (size_t)n * p->img_elems, cudaMemcpyHostToDevice, st));
+      int rcu = u8_to_f32(p->d_u8[slot], p->d_src[slot], (size_t)n * p->img_elems, st);
+      if (rcu) return rcu;
+    } else {
+      RD_CUDA(cudaMemcpyAsync(p->d_src[slot], src_host + off, bytes, cudaMemcpyHostToDevice, st));
+    }
     RD_CUDA(cudaMemcpyAsync(p->d_pidx[slot], partner_idx_host + i0, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
     RD_CUDA(cudaMemcpyAsync(p->d_rk[slot], ratio_k_host + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     int rc = ramdsir_mix_f32(p->d_src[slot], bank_dev, p->d_pidx[slot], p->d_rk[slot], p->d_out[slot], n, p->C, p->H,

@@ -44,10 +44,12 @@ class HostPipeline:
             _lib.check(self._lib.ramdsir_pipe_create(ctypes.byref(self._h), self.chunk, self.C, self.H, self.W, self.b))
 
     def mix(self, src_host, bank: torch.Tensor, partner_idx, ratio_k, out_host, epilogue=NO_EPILOGUE, ratio_den: int = 10):
-        """src_host/out_host: [B, C, H, W] float32 host buffers (pin them for async copies); returns out_host."""
+        """src_host: [B, C, H, W] float32 -- or uint8 (fundus loaders hold uint8 images: a quarter of the H2D bytes,
+        widened on the device); out_host: float32 [B, C, H, W].  Pin both for async copies.  Returns out_host."""
         if self._h is None:
             raise RuntimeError("pipeline is closed")
-        sp, sn = _host_ptr(src_host, "src_host", np.float32)
+        is_u8 = (src_host.dtype == np.uint8) if isinstance(src_host, np.ndarray) else (src_host.dtype == torch.uint8)
+        sp, sn = _host_ptr(src_host, "src_host", np.uint8 if is_u8 else np.float32)
         op, on = _host_ptr(out_host, "out_host", np.float32)
         per = self.C * self.H * self.W
         if sn % per or sn != on:
@@ -64,9 +66,9 @@ class HostPipeline:
         lo, hi, scale, shift = epilogue
         with torch.cuda.device(self.device):
             torch.cuda.current_stream().synchronize()      # the bank may still be in flight on torch's stream
-            _lib.check(self._lib.ramdsir_mix_host_f32(self._h, sp, bank.data_ptr(), pidx.ctypes.data, rk.ctypes.data, op,
-                                                      bsz, bank.shape[0], int(ratio_den), float(lo), float(hi),
-                                                      float(scale), float(shift)))
+            fn = self._lib.ramdsir_mix_host_u8 if is_u8 else self._lib.ramdsir_mix_host_f32
+            _lib.check(fn(self._h, sp, bank.data_ptr(), pidx.ctypes.data, rk.ctypes.data, op, bsz, bank.shape[0],
+                          int(ratio_den), float(lo), float(hi), float(scale), float(shift)))
         return out_host
 
     def close(self):

@@ -413,5 +413,10 @@ def test_host_pipeline_matches_device_path(R):
         assert torch.equal(out, want)
         with pytest.raises(Exception):
             pipe.mix(src, bank, np.full(B, nbank), rk, out)  # out-of-range partner index is refused on the host
+        # uint8 ingestion (ramdsir_mix_host_u8): same result from a quarter of the host->device bytes
+        src_u8 = src.to(torch.uint8).pin_memory()
+        out_u8 = torch.empty_like(src).pin_memory()
+        pipe.mix(src_u8, bank, pidx, rk, out_u8, epilogue=O.FUNDUS_EPILOGUE)
+        assert torch.equal(out_u8, want)
     empty = torch.empty(0, C, H, W, device="cuda")
     assert R.ram_mix_batch(empty, bank, [], []).shape == (0, C, H, W)
