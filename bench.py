@@ -38,6 +38,8 @@ L = 0.1
 WORKLOADS = {
     "fundus": dict(C=3, H=256, W=256, BATCH=256, N_BANK=768, N_DOMAINS=3, EPI="fundus", LO=0, HI=256,
                    NAME="fundus RAM batch 256x3x256x256 fp32, L=0.1 (b=25), 3 source domains, clip[0,255]/127.5-1"),
+    "fundus1024": dict(C=3, H=256, W=256, BATCH=1024, N_BANK=768, N_DOMAINS=3, EPI="fundus", LO=0, HI=256,
+                       NAME="fundus RAM, per-rank shard of BASELINE configs[3] (8192 images / 8 GPUs): 1024x3x256x256 fp32, L=0.1"),
     "prostate": dict(C=1, H=384, W=384, BATCH=512, N_BANK=640, N_DOMAINS=5, EPI="prostate", LO=-1, HI=1,
                      NAME="prostate RAM batch 512x1x384x384 fp32, L=0.1 (b=38), 5 source domains, clip[-1,1]"),
     "prostate3": dict(C=3, H=384, W=384, BATCH=128, N_BANK=320, N_DOMAINS=5, EPI="prostate", LO=-1, HI=1,
