@@ -131,6 +131,20 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
   for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
     const float4* x4 = reinterpret_cast<const float4*>(src + plane * plane_px);
     auto ld_first = [&](size_t off) { return BANK ? __ldg(x4 + off) : ldg_policy(x4 + off, pol_keep); };
+    Epilogue epp = ep;
+    float omr = 0.f;
+    const float* patch = nullptr;
+    if (!BANK) {
+      const int img = plane / C, ch = plane - img * C;
+      const long long p = pidx[img];
+      const bool ok = (p >= 0 && p < (long long)n_bank);
+      if (!ok) epp.scale = __int_as_float(0x7fc00000);   // poison the plane (fminf/fmaxf swallow a NaN delta)
+      omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
+      patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
+      // pull the partner's patch (10-24 KB) towards L2 now; it is consumed after the forward columns
+      const char* pl = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(patch) & ~(uintptr_t)127);
+      if (tid * 128 < (int)(patch_px * 4) + 128) prefetch_l2(pl + tid * 128);
+    }
     // ---- forward columns ----
     for (int strip = 0; strip < CFG::nstrips; ++strip) {
       cf va[16], vb[16];
@@ -144,19 +158,29 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
         __syncthreads();
       }
     }
-    // ---- forward rows on the band rows; meanwhile stage the partner patch / prefetch the next plane ----
-    Epilogue epp = ep;
-    float omr = 0.f;
+    // ---- forward rows on the band rows.  The partner patch is staged around them: its loads are issued first,
+    //      the row transforms run while they are in flight, the symmetrised values are stored afterwards ----
+    constexpr int PPT = ((int)patch_px + NT - 1) / NT;      // patch elements per thread
+    float pv[PPT], pm[PPT];
     if (!BANK) {
-      const int img = plane / C, ch = plane - img * C;
-      const long long p = pidx[img];
-      const bool ok = (p >= 0 && p < (long long)n_bank);
-      if (!ok) epp.scale = __int_as_float(0x7fc00000);   // poison the plane (fminf/fmaxf swallow a NaN delta)
-      omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
-      const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
-      for (int i = tid; i < (int)patch_px; i += NT) s_stage_patch<CFG>(sm, patch, i);
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int i = tid + k * NT;
+        if (i < (int)patch_px) {
+          pv[k] = __ldg(patch + i);
+          pm[k] = __ldg(patch + ((int)patch_px - 1 - i));
+        }
+      }
     }
     for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) s_row_fwd<CFG>(sm, r);
+    if (!BANK) {
+      float* P = reinterpret_cast<float*>(sm + CFG::offP);
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int i = tid + k * NT;
+        if (i < (int)patch_px) P[i] = 0.5f * (pv[k] + pm[k]);    // Re(ifft2) only sees the +-k average
+      }
+    }
     __syncthreads();
     if (BANK) {
       float* patch = out + plane * patch_px;
