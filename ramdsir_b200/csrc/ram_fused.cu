@@ -146,16 +146,42 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
       if (tid * 128 < (int)(patch_px * 4) + 128) prefetch_l2(pl + tid * 128);
     }
     // ---- forward columns ----
-    for (int strip = 0; strip < CFG::nstrips; ++strip) {
-      cf va[16], vb[16];
-      s_f1_load_fft_tw<CFG>(ld_first, sm, strip, tid, va, vb);
-      if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
+    if constexpr (CFG::smemBytes > 113 * 1024) {
+      // one CTA per SM (384^2): registers are not capped at 128, so rows j = 0..7 of the next strip are requested
+      // one stage early (32 registers in flight across the last exchange stage): the 64 KB load burst of a strip
+      // is split in two (+1 % measured).  At two CTAs per SM the same trick spills and loses 4 %.
+      float4 lo[8];
+      s_f1_load_rows<CFG, 0>(ld_first, 0, tid, lo);
+      for (int strip = 0; strip < CFG::nstrips; ++strip) {
+        cf va[16], vb[16];
+        {
+          float4 hi[8];
+          s_f1_load_rows<CFG, 8>(ld_first, strip, tid, hi);
+          if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
+          s_f1_fft_tw_raw<CFG>(sm, tid, lo, hi, va, vb);
+        }
+        s_f1_store_half<CFG>(sm, tid, 0, va, vb);
+        __syncthreads();
+        for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, 0, u);
+        __syncthreads();
+        s_f1_store_half<CFG>(sm, tid, 1, va, vb);
+        if (strip + 1 < CFG::nstrips) s_f1_load_rows<CFG, 0>(ld_first, strip + 1, tid, lo);
+        __syncthreads();
+        for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, 1, u);
+        __syncthreads();
+      }
+    } else {
+      for (int strip = 0; strip < CFG::nstrips; ++strip) {
+        cf va[16], vb[16];
+        s_f1_load_fft_tw<CFG>(ld_first, sm, strip, tid, va, vb);
+        if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        s_f1_store_half<CFG>(sm, tid, half, va, vb);
-        __syncthreads();
-        for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, half, u);
-        __syncthreads();
+        for (int half = 0; half < 2; ++half) {
+          s_f1_store_half<CFG>(sm, tid, half, va, vb);
+          __syncthreads();
+          for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, half, u);
+          __syncthreads();
+        }
       }
     }
     // ---- forward rows on the band rows.  The partner patch is staged around them: its loads are issued first,

@@ -80,6 +80,41 @@ RD_HD void s_f1_load_fft_tw(LoadF4 ld, const unsigned char* sm, int strip, int t
   }
 }
 
+// Half-ahead variant of F1a: rows j = 0..7 of a strip are loaded one stage early (s_f1_load_rows<0>), rows
+// j = 8..15 at the start of the strip (s_f1_load_rows<8>); s_f1_fft_tw_raw then transforms and twiddles.
+template <class CFG, int JBASE, class LoadF4>
+RD_HD void s_f1_load_rows(LoadF4 ld, int strip, int t, float4 (&raw)[8]) {
+  const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) raw[j] = ld((size_t)(h1 + CFG::N1h * (JBASE + j)) * CFG::M + c4);
+}
+
+template <class CFG>
+RD_HD void s_f1_fft_tw_raw(const unsigned char* sm, int t, const float4 (&lo)[8], const float4 (&hi)[8], cf (&va)[16], cf (&vb)[16]) {
+  const int h1 = t >> 4;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    va[j] = cf{lo[j].x, lo[j].z};
+    vb[j] = cf{lo[j].y, lo[j].w};
+    va[j + 8] = cf{hi[j].x, hi[j].z};
+    vb[j + 8] = cf{hi[j].y, hi[j].w};
+  }
+  fft16<-1>(va);
+  fft16<-1>(vb);
+  const float4* tw = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWH) +
+                     h1 * (CFG::twhPitch / 2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 w = tw[i];
+    if (i > 0) {
+      va[pos16(2 * i)] = cmul(va[pos16(2 * i)], cf{w.x, w.y});
+      vb[pos16(2 * i)] = cmul(vb[pos16(2 * i)], cf{w.x, w.y});
+    }
+    va[pos16(2 * i + 1)] = cmul(va[pos16(2 * i + 1)], cf{w.z, w.w});
+    vb[pos16(2 * i + 1)] = cmul(vb[pos16(2 * i + 1)], cf{w.z, w.w});
+  }
+}
+
 // ---- F1b: publish k2 in [8 half, 8 half + 8) to E[k2l][h1][c] ---------------------------------------
 template <class CFG>
 RD_HD void s_f1_store_half(unsigned char* sm, int t, int half, const cf (&va)[16], const cf (&vb)[16]) {
