@@ -239,11 +239,22 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
         __syncthreads();
         s_inv_fft8<CFG>(sm, tid, 0, eva, evb);
         __syncthreads();
-        for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 1, u);
-        __syncthreads();
-        s_inv_fft8<CFG>(sm, tid, 1, oda, odb);
-        __syncthreads();
-        s_inv_combine_store<CFG>(ld_again, st, epp, strip, tid, eva, evb, oda, odb);
+        if constexpr (CFG::smemBytes > 113 * 1024) {
+          // one CTA per SM: request half of the strip's x quads before the second-parity stage
+          float4 xpre[8];
+          s_inv_preload_x<CFG>(ld_again, strip, tid, xpre);
+          for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 1, u);
+          __syncthreads();
+          s_inv_fft8<CFG>(sm, tid, 1, oda, odb);
+          __syncthreads();
+          s_inv_combine_store_pre<CFG>(ld_again, st, epp, strip, tid, xpre, eva, evb, oda, odb);
+        } else {
+          for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 1, u);
+          __syncthreads();
+          s_inv_fft8<CFG>(sm, tid, 1, oda, odb);
+          __syncthreads();
+          s_inv_combine_store<CFG>(ld_again, st, epp, strip, tid, eva, evb, oda, odb);
+        }
       }
     }
     // next plane: its first E write happens after its loads and Z is only rewritten two barriers later

@@ -276,6 +276,50 @@ struct Combine<CFG, 8> {
   static RD_HD void run(LoadF4, StoreF4, Epilogue, size_t, const cf (&)[8], const cf (&)[8], const cf (&)[8], const cf (&)[8]) {}
 };
 
+// Variant with the x quads of rows J = 0..3 (both halves) preloaded one stage early (xpre[2 J + hi]).
+template <class CFG, int J>
+struct CombineP {
+  template <class LoadF4, class StoreF4>
+  static RD_HD void run(LoadF4 ld, StoreF4 st, Epilogue ep, size_t base, const float4 (&xpre)[8], const cf (&eva)[8],
+                        const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
+    const cf wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
+    const cf ea = eva[pos8(J)], eb = evb[pos8(J)];
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const size_t off = base + (size_t)(CFG::N1h * (J + 8 * hi)) * CFG::M;
+      const cf a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
+      const float4 x = (J < 4) ? xpre[2 * (J & 3) + hi] : ld(off);
+      float4 y;
+      y.x = fmaf(fminf(fmaxf(x.x + a.re, ep.lo), ep.hi), ep.scale, ep.shift);
+      y.y = fmaf(fminf(fmaxf(x.y + bq.re, ep.lo), ep.hi), ep.scale, ep.shift);
+      y.z = fmaf(fminf(fmaxf(x.z + a.im, ep.lo), ep.hi), ep.scale, ep.shift);
+      y.w = fmaf(fminf(fmaxf(x.w + bq.im, ep.lo), ep.hi), ep.scale, ep.shift);
+      st(off, y, x);
+    }
+    CombineP<CFG, J + 1>::run(ld, st, ep, base, xpre, eva, evb, oda, odb);
+  }
+};
+template <class CFG>
+struct CombineP<CFG, 8> {
+  template <class LoadF4, class StoreF4>
+  static RD_HD void run(LoadF4, StoreF4, Epilogue, size_t, const float4 (&)[8], const cf (&)[8], const cf (&)[8],
+                        const cf (&)[8], const cf (&)[8]) {}
+};
+
+template <class CFG, class LoadF4>
+RD_HD void s_inv_preload_x(LoadF4 ld, int strip, int t, float4 (&xpre)[8]) {
+  const size_t base = (size_t)(t >> 4) * CFG::M + strip * 16 + (t & 15);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xpre[i] = ld(base + (size_t)(CFG::N1h * ((i >> 1) + 8 * (i & 1))) * CFG::M);
+}
+
+template <class CFG, class LoadF4, class StoreF4>
+RD_HD void s_inv_combine_store_pre(LoadF4 ld, StoreF4 st, Epilogue ep, int strip, int t, const float4 (&xpre)[8],
+                                   const cf (&eva)[8], const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
+  const size_t base = (size_t)(t >> 4) * CFG::M + strip * 16 + (t & 15);
+  CombineP<CFG, 0>::run(ld, st, ep, base, xpre, eva, evb, oda, odb);
+}
+
 template <class CFG, class LoadF4, class StoreF4>
 RD_HD void s_inv_combine_store(LoadF4 ld, StoreF4 st, Epilogue ep, int strip, int t, const cf (&eva)[8],
                                const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
