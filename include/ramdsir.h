@@ -17,7 +17,7 @@
  *
  * Conventions
  *   - plain C, no C++/torch types; all *_dev pointers are BORROWED device pointers on the current
- *     CUDA device, 16-byte aligned, densely packed NCHW float32; `stream` is a cudaStream_t cast to
+ *     CUDA device, densely packed NCHW float32 (16-byte aligned unless the shape runs on the generic kernels); `stream` is a cudaStream_t cast to
  *     void* (NULL = legacy default stream).  Calls are asynchronous and stream-ordered.
  *   - the library owns nothing persistent except per-(device, H, W, b) twiddle tables built lazily
  *     on first use (a few KB each) and, for the *_host entry, an explicit pipeline handle.

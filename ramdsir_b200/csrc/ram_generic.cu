@@ -246,7 +246,35 @@ int get_tw(int N, float2** out) {
 
 size_t per_plane_bytes(int H, int b) { return ((size_t)H * (b + 1) + (size_t)(2 * b + 1) * (b + 1)) * sizeof(float2); }
 
+// images per internal chunk: grid.y <= 65535 planes, and at most ~256 MB of workspace
+int chunk_images(int C, int H, int b) {
+  size_t n = 65535 / (size_t)C;
+  const size_t by_ws = ((size_t)256 << 20) / ((size_t)C * per_plane_bytes(H, b));
+  if (by_ws < n) n = by_ws;
+  return n < 1 ? 1 : (int)n;
+}
+
+int run_chunk(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, size_t ws_bytes, cudaStream_t st);
+
 int run(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int per = chunk_images(a.C, a.H, a.b);
+  const size_t img_px = (size_t)a.C * a.H * a.W, patch_px = (size_t)a.C * (2 * a.b + 1) * (2 * a.b + 1);
+  for (int i0 = 0; i0 < nimg; i0 += per) {
+    const int n = nimg - i0 < per ? nimg - i0 : per;
+    MixArgs c = a;
+    c.src = a.src + (size_t)i0 * img_px;
+    if (!bank_mode) {
+      c.out = a.out + (size_t)i0 * img_px;
+      c.pidx = a.pidx + i0;
+      c.rk = a.rk + i0;
+    }
+    const int rc = run_chunk(bank_mode, c, bank_mode ? bank_out + (size_t)i0 * patch_px : nullptr, n, ws, ws_bytes, st);
+    if (rc) return rc;
+  }
+  return RAMDSIR_OK;
+}
+
+int run_chunk(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int H = a.H, W = a.W, b = a.b, C = a.C;
   const size_t planes = (size_t)nimg * C;
   if (planes == 0) return RAMDSIR_OK;
@@ -254,10 +282,6 @@ int run(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, s
   if (ws == nullptr || ws_bytes < need) {
     set_error("generic path needs %zu workspace bytes, got %zu", need, ws_bytes);
     return RAMDSIR_ERR_WORKSPACE;
-  }
-  if (planes > 65535) {
-    set_error("generic path handles at most 65535 planes per call, got %zu", planes);
-    return RAMDSIR_ERR_UNSUPPORTED;
   }
   float2 *twH, *twW;
   int rc = get_tw(H, &twH);
@@ -392,7 +416,8 @@ bool generic_supported(int H, int W, int b) {
 
 size_t generic_workspace_bytes(int n_images, int C, int H, int W, int b) {
   (void)W;
-  return (size_t)n_images * C * per_plane_bytes(H, b);
+  const int per = chunk_images(C, H, b);
+  return (size_t)(n_images < per ? n_images : per) * C * per_plane_bytes(H, b);
 }
 
 int generic_mix(const MixArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) { return run(false, a, nullptr, a.B, ws, ws_bytes, st); }

@@ -103,8 +103,12 @@ int ramdsir_bank_build_f32(const float* imgs_dev, float* bank_dev, int N, int C,
   int rc = check_shape(N, C, H, W, b);
   if (rc) return rc;
   if (N == 0) return RAMDSIR_OK;
-  if (!imgs_dev || !bank_dev || !aligned16(imgs_dev)) {
-    set_error("bank_build: null or misaligned pointer");
+  if (!imgs_dev || !bank_dev) {
+    set_error("bank_build: null pointer");
+    return RAMDSIR_ERR_INVALID;
+  }
+  if (path_of(H, W, b) != RAMDSIR_PATH_GENERIC && !aligned16(imgs_dev)) {   // the float4 paths need 16-byte alignment
+    set_error("bank_build: imgs must be 16-byte aligned for this shape");
     return RAMDSIR_ERR_INVALID;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -140,8 +144,12 @@ int ramdsir_mix_dual_f32(const float* src_dev, const float* bank_dev, const int6
   int rc = check_shape(B, C, H, W, b);
   if (rc) return rc;
   if (B == 0) return RAMDSIR_OK;
-  if (!src_dev || !bank_dev || !partner_idx_dev || !ratio_k_dev || !out_dev || !aligned16(src_dev) || !aligned16(out_dev)) {
-    set_error("mix: null or misaligned pointer");
+  if (!src_dev || !bank_dev || !partner_idx_dev || !ratio_k_dev || !out_dev) {
+    set_error("mix: null pointer");
+    return RAMDSIR_ERR_INVALID;
+  }
+  if (path_of(H, W, b) != RAMDSIR_PATH_GENERIC && (!aligned16(src_dev) || !aligned16(out_dev))) {
+    set_error("mix: src and out must be 16-byte aligned for this shape (float4 kernels)");
     return RAMDSIR_ERR_INVALID;
   }
   if (n_bank < 1 || ratio_den < 1) {
@@ -157,7 +165,7 @@ int ramdsir_mix_dual_f32(const float* src_dev, const float* bank_dev, const int6
   a.independent = (flags & RAMDSIR_FLAG_INDEPENDENT) != 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (clean_out_dev) {
-    if (!aligned16(clean_out_dev) || clean_out_dev == out_dev || clean_out_dev == src_dev) {
+    if ((path_of(H, W, b) != RAMDSIR_PATH_GENERIC && !aligned16(clean_out_dev)) || clean_out_dev == out_dev || clean_out_dev == src_dev) {
       set_error("mix_dual: clean_out must be 16-byte aligned and distinct from src and out");
       return RAMDSIR_ERR_INVALID;
     }

@@ -66,6 +66,8 @@ def test_invalid_arguments_return_codes_not_crashes(lib):
     rc = lib.ramdsir_mix_f32(None, None, None, None, None, 4, 3, 256, 256, 25, 1, 10, 0.0, 1.0, 1.0, 0.0, None, 0, None)
     assert rc == _lib.ERR_INVALID
     assert b"null" in lib.ramdsir_last_error()
+    rc = lib.ramdsir_mix_f32(8, 16, 16, 16, 32, 4, 3, 256, 256, 25, 1, 10, 0.0, 1.0, 1.0, 0.0, None, 0, None)
+    assert rc == _lib.ERR_INVALID and b"aligned" in lib.ramdsir_last_error()      # float4 kernels need 16-byte alignment
     rc = lib.ramdsir_bank_build_f32(None, None, 4, 3, 64, 64, 40, None, 0, None)
     assert rc == _lib.ERR_UNSUPPORTED
     assert lib.ramdsir_force_path(7) == _lib.ERR_INVALID

@@ -303,6 +303,23 @@ def test_shape_mismatch_raises(R):
         R.ram_mix_batch(torch.zeros(1, 1, 64, 64, device="cuda"), torch.zeros(1, 1, 65, 65, device="cuda"), [0], [5], L=0.5)
 
 
+def test_generic_path_chunks_large_batches(R):
+    """More planes than one grid can index (65 535) and more than the workspace cap: the generic path loops over
+    image chunks internally and every image still equals the single-image result."""
+    B, C, H, W = 70000, 1, 9, 11
+    g = torch.Generator(device="cuda").manual_seed(1)
+    src = torch.rand(B, C, H, W, device="cuda", generator=g)
+    bank = R.build_amp_bank(torch.rand(4, C, H, W, device="cuda", generator=g), L=0.2)
+    pidx = torch.arange(B, device="cuda") % 4
+    rk = (torch.arange(B, device="cuda") % 10 + 1).to(torch.int32)
+    out = R.ram_mix_batch(src, bank, pidx, rk, L=0.2)
+    for i in (0, 65534, 65535, 65536, B - 1):
+        one = R.ram_mix_batch(src[i:i + 1].contiguous(), bank, pidx[i:i + 1], rk[i:i + 1], L=0.2)
+        assert torch.equal(one[0], out[i])
+    big_bank = R.build_amp_bank(src, L=0.2)
+    assert torch.equal(big_bank[65540], R.build_amp_bank(src[65540:65541].contiguous(), L=0.2)[0])
+
+
 def test_device_side_bad_partner_poisons_with_nan(R):
     src = torch.rand(2, 1, 64, 64, device="cuda")
     bank = R.build_amp_bank(torch.rand(3, 1, 64, 64, device="cuda"))
