@@ -112,21 +112,32 @@ def _cpu_init(seed):
     _CPU["epi"] = O.FUNDUS_EPILOGUE if EPI_NAME == "fundus" else O.PROSTATE_EPILOGUE
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def _cpu_work(args):
     """One image exactly as Fundus_Multi.__getitem__ does it (fundus.py:213-223): partner amplitude,
     mix, clip, normalise.  float64 path (= numpy 1.x behaviour, the parity oracle)."""
-    i, pidx, rk = args
+    i, pidx, rk = args[:3]
+    precision = args[3] if len(args) > 3 else "f64"
     O = _CPU["O"]
-    y = O.mix_batch(_CPU["src"][i % 8][None], _CPU["par"], [pidx % 8], [rk], L, epi=_CPU["epi"])
+    y = O.mix_batch(_CPU["src"][i % 8][None], _CPU["par"], [pidx % 8], [rk], L, epi=_CPU["epi"], precision=precision)
     return float(y[0, 0, 0, 0])
 
 
-def cpu_images_per_s(n_images, cores, reps=1):
+def cpu_images_per_s(n_images, cores, reps=1, precision="f64"):
     """Images/s of the oracle on `cores` worker processes (the reference's DataLoader worker model,
     train.py:558-559); pool start-up excluded.  Returns (best img/s, list of per-rep seconds)."""
     import multiprocessing as mp
     pidx, rk = draw_selection(n_images, N_BANK, SEED)
-    jobs = [(i, int(pidx[i]), int(rk[i])) for i in range(n_images)]
+    jobs = [(i, int(pidx[i]), int(rk[i]), precision) for i in range(n_images)]
     times = []
     if cores == 1:
         _cpu_init(SEED)
@@ -173,7 +184,7 @@ def run_reference_arm(args, rank, world):
                          "sample": "%d images/step x %d steps, float64 numpy path, multiprocessing.Pool(%d)"
                                    % (sample, args.steps, cores)},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "numpy": np.__version__,
+        "gpu_launches": 0, "numpy": np.__version__, "cpu_model": cpu_model(),
     }
     print(json.dumps(line), flush=True)
 
@@ -401,10 +412,13 @@ def run_ours(args, rank, local_rank, world):
             n = max(64, cores * 8)
             ips, times = cpu_images_per_s(n, cores, reps=2)
             ips1, _ = cpu_images_per_s(16, 1, reps=1)
+            ips32, _ = cpu_images_per_s(n, cores, reps=1, precision="native")
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": "%d images of the workload x2 reps (best), float64 numpy path, "
                                               "multiprocessing.Pool(%d)" % (n, cores),
-                                    "single_core_images_per_s": ips1, "numpy": np.__version__}
+                                    "single_core_images_per_s": ips1,
+                                    "native_float32_path_images_per_s": ips32,   # what numpy >= 2 does with float32 input
+                                    "cpu_model": cpu_model(), "numpy": np.__version__}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
