@@ -125,9 +125,11 @@ ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank, const int
     }
   }
   __syncthreads();
-  for (int t = tid; t < ng * 2 * M; t += NT) {
-    const int g = t / (2 * M), tt = t % (2 * M);
-    if (live(2 * g + tt / M)) m_fill_v<CFG>(R + (size_t)g * RP, D + g * DP, tab, kh0 + g, tt / M, tt % M);
+  for (int i = tid; i < ng * RP; i += NT) R[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // everything off the band is zero
+  __syncthreads();
+  for (int t = tid; t < ng * 2 * CFG::nb; t += NT) {
+    const int g = t / (2 * CFG::nb), tt = t % (2 * CFG::nb), srow = tt / CFG::nb;
+    if (live(2 * g + srow)) m_put_v<CFG>(R + (size_t)g * RP, D + g * DP, tab, kh0 + g, srow, tt % CFG::nb);
   }
   __syncthreads();
   for (int t = tid; t < ng * 32; t += NT) {

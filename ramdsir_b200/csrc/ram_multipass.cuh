@@ -47,7 +47,7 @@ struct KCfg {
   static constexpr int bOffD = s_al16(KG * 2 * rowPitch * 16); // [KG][2][b+1] float2
   static constexpr int bOffP = bOffD + s_al16(KG * 2 * (B_ + 1) * 8);   // [KG][2][nb] float: partner patch rows b+kh, b-kh
   static constexpr int bOffTab = bOffP + s_al16(KG * 2 * nb * 4);
-  static constexpr int tTWM = 0;                               // [N1w][16] float2  W_M^(c1 k2)
+  static constexpr int tTWM = 0;                               // [16][N1w] float2  W_M^(c1 k2), k2-major
   static constexpr int tTW3 = tTWM + N1w * 16 * 2;             // [3][b+1] float2   W_W^(g kw)
   static constexpr int tQ = ((tTW3 + 3 * (B_ + 1) * 2) + 3) & ~3;   // [nb] float4: (Qa, Qb)[kw]
   static constexpr int bTabBytes = s_al16((tQ + nb * 4) * 4);
@@ -198,7 +198,7 @@ template <class CFG, int DIR>
 RD_HD void m_row_stage1(float4* Rbase, const float* tab, int task) {
   const int row = task / CFG::N1w, c1 = task % CFG::N1w;
   float4* R = Rbase + (size_t)row * CFG::rowPitch + c1;
-  const float2* tw = reinterpret_cast<const float2*>(tab + CFG::tTWM) + c1 * 16;
+  const float2* tw = reinterpret_cast<const float2*>(tab + CFG::tTWM) + c1;   // TWM is stored [k2][c1]: lanes <-> c1 read contiguously
   cf va[16], vb[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -206,7 +206,7 @@ RD_HD void m_row_stage1(float4* Rbase, const float* tab, int task) {
     va[j] = cf{q.x, q.y};
     vb[j] = cf{q.z, q.w};
     if (DIR > 0) {   // inverse: undo the twiddle first (input index is k2)
-      const float2 w = tw[j];
+      const float2 w = tw[j * CFG::N1w];
       va[j] = cmulc(va[j], cf{w.x, w.y});
       vb[j] = cmulc(vb[j], cf{w.x, w.y});
     }
@@ -217,7 +217,7 @@ RD_HD void m_row_stage1(float4* Rbase, const float* tab, int task) {
   for (int k = 0; k < 16; ++k) {
     cf a = va[pos16(k)], bq = vb[pos16(k)];
     if (DIR < 0) {
-      const float2 w = tw[k];
+      const float2 w = tw[k * CFG::N1w];
       a = cmul(a, cf{w.x, w.y});
       bq = cmul(bq, cf{w.x, w.y});
     }
@@ -291,24 +291,19 @@ RD_HD void m_band(const float4* R, float2* D, const float* tab, const float* pat
   D[srow * (CFG::b + 1) + kw] = make_float2(d.re, d.im);
 }
 
-// Fill row `srow` with the inverse-side packed spectrum V{a,b}[kw] = dF[s kh][kw] * (Qa, Qb)[kw] (zero off the band).
+// Write the inverse-side packed spectrum V{a,b}[kw] = dF[s kh][kw] * (Qa, Qb)[kw] of band bin kw = kwi - b into its
+// slot of row `srow` (the row has been zero-filled; lanes walk consecutive kw: D and Q reads are contiguous and the
+// slot stride SP is conflict-free).
 template <class CFG>
-RD_HD void m_fill_v(float4* R, const float2* D, const float* tab, int kh, int srow, int slot_idx) {
-  // slot_idx enumerates the M slots of the row; slot = N1w k2 + q  <->  kw = k2 + 16 q (mod M, centred)
-  const int k2 = slot_idx / CFG::N1w, q = slot_idx % CFG::N1w;
-  int kw = k2 + 16 * q;
-  if (kw >= CFG::M / 2) kw -= CFG::M;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (kw >= -CFG::b && kw <= CFG::b) {
-    const int other = (kh == 0) ? 0 : 1 - srow;
-    cf d;
-    if (kw >= 0) { const float2 t = D[srow * (CFG::b + 1) + kw]; d = cf{t.x, t.y}; }
-    else { const float2 t = D[other * (CFG::b + 1) - kw]; d = cf{t.x, -t.y}; }   // dF[-k] = conj dF[k]
-    const float4 qq = reinterpret_cast<const float4*>(tab + CFG::tQ)[kw + CFG::b];
-    const cf a = cmul(d, cf{qq.x, qq.y}), bq = cmul(d, cf{qq.z, qq.w});
-    v = make_float4(a.re, a.im, bq.re, bq.im);
-  }
-  R[(size_t)srow * CFG::rowPitch + CFG::SP * k2 + q] = v;
+RD_HD void m_put_v(float4* R, const float2* D, const float* tab, int kh, int srow, int kwi) {
+  const int kw = kwi - CFG::b;
+  const int other = (kh == 0) ? 0 : 1 - srow;
+  cf d;
+  if (kw >= 0) { const float2 t = D[srow * (CFG::b + 1) + kw]; d = cf{t.x, t.y}; }
+  else { const float2 t = D[other * (CFG::b + 1) - kw]; d = cf{t.x, -t.y}; }   // dF[-k] = conj dF[k]
+  const float4 qq = reinterpret_cast<const float4*>(tab + CFG::tQ)[kwi];
+  const cf a = cmul(d, cf{qq.x, qq.y}), bq = cmul(d, cf{qq.z, qq.w});
+  R[(size_t)srow * CFG::rowPitch + m_slot<CFG>(kw)] = make_float4(a.re, a.im, bq.re, bq.im);
 }
 
 }  // namespace ramdsir

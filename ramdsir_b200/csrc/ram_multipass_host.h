@@ -27,8 +27,8 @@ inline void multipass_tables_b(float* tab) {    // pass B: TWM, TW3, Q
   for (int c1 = 0; c1 < CFG::N1w; ++c1)
     for (int k2 = 0; k2 < 16; ++k2) {
       const long n = ((long)c1 * k2) % CFG::M;
-      tab[CFG::tTWM + 2 * (c1 * 16 + k2)] = (float)ct::cos2pi(n, CFG::M);
-      tab[CFG::tTWM + 2 * (c1 * 16 + k2) + 1] = (float)-ct::sin2pi(n, CFG::M);
+      tab[CFG::tTWM + 2 * (k2 * CFG::N1w + c1)] = (float)ct::cos2pi(n, CFG::M);
+      tab[CFG::tTWM + 2 * (k2 * CFG::N1w + c1) + 1] = (float)-ct::sin2pi(n, CFG::M);
     }
   for (int g = 1; g <= 3; ++g)
     for (int kw = 0; kw <= CFG::b; ++kw) {

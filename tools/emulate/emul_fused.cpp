@@ -339,7 +339,8 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
         }
         for (int t = 0; t < nrows * (CFG::b + 1); ++t)
           m_band<CFG, false>(R, D, tab, prow.data(), nullptr, omr, kh, t / (CFG::b + 1), t % (CFG::b + 1));
-        for (int t = 0; t < nrows * CFG::M; ++t) m_fill_v<CFG>(R, D, tab, kh, t / CFG::M, t % CFG::M);
+        for (int t = 0; t < 2 * CFG::rowPitch; ++t) R[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < nrows * CFG::nb; ++t) m_put_v<CFG>(R, D, tab, kh, t / CFG::nb, t % CFG::nb);
         for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, 1>(R, t);
         for (int t = 0; t < nrows * CFG::N1w; ++t) m_row_stage1<CFG, 1>(R, tab, t);
         for (int r = 0; r < nrows; ++r)
