@@ -541,7 +541,10 @@ template <int MMAX, bool BANK>
 int launch(const FusedPlan& p, const float* src, const float* bank, const int64_t* pidx, const int32_t* rk,
            int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
   auto kern = ram_fused_kernel<MMAX, BANK>;
-  static thread_local int configured_smem = -1;  // per instantiation
+  static thread_local int configured_smem_dev[64];  // per (instantiation, device); zero-initialised
+  int dev = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  int& configured_smem = configured_smem_dev[dev & 63];
   if (configured_smem < p.S.smemBytes) {
     RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.S.smemBytes));
     configured_smem = p.S.smemBytes;
@@ -583,7 +586,11 @@ int launch_static(const FusedPlan& p, const float* src, const float* bank, const
   if constexpr (KernelOf<CFG, BANK>::dual) {
     if (t_clean && !BANK) kern = KernelOf<CFG, BANK>::get_dual();
   }
-  static thread_local int per_sm = 0;  // per instantiation
+  // cudaFuncSetAttribute and occupancy are per device: cache per (instantiation, device)
+  static thread_local int per_sm_dev[64] = {0};
+  int dev = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  int& per_sm = per_sm_dev[dev & 63];
   if (per_sm == 0) {
     RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
     if constexpr (KernelOf<CFG, BANK>::dual)
