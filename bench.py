@@ -334,6 +334,29 @@ def run_ours(args, rank, local_rank, world):
         e1.record()
         torch.cuda.synchronize()
         serial_ms = e0.elapsed_time(e1) / args.steps
+    # uint8-resident sources (what a fundus loader actually holds, fundus.py:205-214): the kernel reads the bytes
+    # itself, 5 instead of 8 algorithmic bytes per pixel.  Same K steps, same launch mode; reported beside the headline.
+    u8_src = None
+    if EPI_NAME == "fundus" and R.u8_supported(C, H, W, b):
+        src_u8d = src.to(torch.uint8)
+        o8 = [torch.empty_like(src) for _ in range(2)]
+        for i in range(3):
+            R.ram_mix_batch(src_u8d, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=o8[i & 1],
+                            independent=not args.serial)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            R.ram_mix_batch(src_u8d, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=o8[i & 1],
+                            independent=not args.serial)
+        e1.record()
+        torch.cuda.synchronize()
+        u8_ms = e0.elapsed_time(e1) / args.steps
+        u8_bytes = (C * H * W * 5 + C * (2 * b + 1) ** 2 * 4) * BATCH
+        u8_src = {"value": BATCH / (u8_ms * 1e-3), "unit": "images/s", "ms_per_step": u8_ms,
+                  "algorithmic_bytes_per_launch": u8_bytes, "achieved": u8_bytes / (u8_ms * 1e-3) / 1e9,
+                  "bit_identical_to_f32_source": bool(torch.equal(o8[0], outs[0])),
+                  "note": "rank 0; ramdsir_mix_dual_u8: sources resident in HBM as uint8 [B,C,H,W], float32 output"}
+        del src_u8d, o8
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -398,6 +421,7 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": serial_ms, "value": BATCH / (serial_ms * 1e-3),
                 "frac": abytes / (serial_ms * 1e-3) / 1e9 / peak,
                 "note": "rank 0, same K steps launched strictly stream-ordered (no overlap between steps)"},
+            "u8_source": None if u8_src is None else dict(u8_src, frac=u8_src["achieved"] / peak),
             "fft_tflops_nominal": nominal_fft_flops_per_image(C, H, W) * value / 1e12,
             "e2e": {"value": e2e_value, "unit": "images/s",
                     "h2d_bytes_per_step": int(src_h.numel() * 4 + pidx_h.nbytes + rk_h.nbytes),

@@ -113,6 +113,22 @@ int ramdsir_mix_dual_f32(const float* src_dev, const float* bank_dev, const int6
                          void* workspace_dev, size_t workspace_bytes, void* stream, unsigned flags);
 
 /*
+ * uint8 sources.  The reference's loaders hand RAM pixels that are uint8-valued (PIL image -> np.array ->
+ * astype(float32), fundus.py:205-214; the bank sources likewise, fundus.py:210-214).  These entry points read the
+ * uint8 planes [.., C, H, W] directly (1 byte instead of 4 per pixel over PCIe and HBM); the arithmetic is the
+ * float32 path's on float(src), so results are BIT-IDENTICAL to ramdsir_mix_dual_f32 / ramdsir_bank_build_f32 on
+ * the converted input.  Available on the static fused kernels only (ramdsir_u8_supported() != 0: 256x256 with
+ * b = 25, 384x384 with b = 38); other shapes return RAMDSIR_ERR_UNSUPPORTED (convert on the device and use the
+ * f32 entry points).  src must be 4-byte aligned, out / clean_out 16-byte aligned; clean_out_dev may be NULL.
+ */
+int ramdsir_u8_supported(int C, int H, int W, int b);
+int ramdsir_bank_build_u8(const uint8_t* imgs_dev, float* bank_dev, int N, int C, int H, int W, int b, void* stream);
+int ramdsir_mix_dual_u8(const uint8_t* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
+                        const int32_t* ratio_k_dev, float* out_dev, float* clean_out_dev, int B, int C, int H, int W,
+                        int b, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
+                        void* stream, unsigned flags);
+
+/*
  * Strict per-sample drop-ins (correctness shims for code that calls the reference functions directly).
  *   ramdsir_amp_spectrum_f32 <- extract_amp_spectrum: FULL amplitude spectrum [N, C, H, W], un-shifted
  *                               (fundus.py:13-19).  Direct DFT, any H and W; workspace from

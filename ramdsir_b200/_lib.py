@@ -24,6 +24,7 @@ PATH_NONE, PATH_FUSED, PATH_MULTIPASS, PATH_GENERIC = 0, 1, 2, 3
 SYMBOLS = [
     "ramdsir_version", "ramdsir_last_error", "ramdsir_band_halfwidth", "ramdsir_path", "ramdsir_force_path", "ramdsir_set_fused_variant",
     "ramdsir_workspace_bytes", "ramdsir_bank_build_f32", "ramdsir_mix_f32", "ramdsir_mix_f32_ex", "ramdsir_mix_dual_f32",
+    "ramdsir_u8_supported", "ramdsir_bank_build_u8", "ramdsir_mix_dual_u8",
     "ramdsir_amp_spectrum_workspace_bytes", "ramdsir_amp_spectrum_f32", "ramdsir_band_blend_f32",
     "ramdsir_pipe_create", "ramdsir_pipe_destroy", "ramdsir_mix_host_f32", "ramdsir_mix_host_u8", "ramdsir_launch_count",
 ]
@@ -74,6 +75,9 @@ def _declare(lib):
     lib.ramdsir_mix_f32.argtypes = ([vp] * 5 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_size_t, vp])
     lib.ramdsir_mix_f32_ex.argtypes = ([vp] * 5 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_size_t, vp, c.c_uint])
     lib.ramdsir_mix_dual_f32.argtypes = ([vp] * 6 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_size_t, vp, c.c_uint])
+    lib.ramdsir_u8_supported.argtypes = [c.c_int] * 4
+    lib.ramdsir_bank_build_u8.argtypes = [vp, vp] + [c.c_int] * 5 + [vp]
+    lib.ramdsir_mix_dual_u8.argtypes = ([vp] * 6 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_uint])
     lib.ramdsir_amp_spectrum_workspace_bytes.argtypes = [c.c_int] * 4
     lib.ramdsir_amp_spectrum_workspace_bytes.restype = c.c_size_t
     lib.ramdsir_amp_spectrum_f32.argtypes = [vp, vp] + [c.c_int] * 4 + [vp, c.c_size_t, vp]

@@ -58,6 +58,22 @@ def _need_cuda_f32(t, name, ndim):
     return t
 
 
+def u8_supported(c: int, h: int, w: int, b: int) -> bool:
+    """True when uint8 sources of this shape are read directly by the RAM kernel (ramdsir_u8_supported)."""
+    return bool(_lib.load().ramdsir_u8_supported(int(c), int(h), int(w), int(b)))
+
+
+def _need_cuda_src(t, name):
+    """Sources may be float32 or uint8 (what the reference's loaders start from, fundus.py:205-214)."""
+    if isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8:
+        if t.dim() != 4:
+            raise ValueError("%s must have 4 dims, got shape %s" % (name, tuple(t.shape)))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous (NCHW)" % name)
+        return t
+    return _need_cuda_f32(t, name, 4)
+
+
 def _workspace(nbytes, device, workspace):
     if nbytes == 0:
         return None, 0, 0
@@ -68,15 +84,17 @@ def _workspace(nbytes, device, workspace):
 
 def build_amp_bank(imgs: torch.Tensor, L: float = 0.1, out: torch.Tensor | None = None, stream=None,
                    workspace: torch.Tensor | None = None) -> torch.Tensor:
-    """imgs [N, C, H, W] float32 CUDA -> bank [N, C, 2b+1, 2b+1] float32 (K3, amplitude-bank builder).
+    """imgs [N, C, H, W] float32 (or uint8) CUDA -> bank [N, C, 2b+1, 2b+1] float32 (K3, amplitude-bank builder).
 
     bank[n, c] == np.fft.fftshift(extract_amp_spectrum(imgs[n]))[c, cH-b:cH+b+1, cW-b:cW+b+1].
     `out` may be a slice of a larger (all-gather) buffer so the collective needs no staging copy.
     """
-    imgs = _need_cuda_f32(imgs, "imgs", 4)
+    imgs = _need_cuda_src(imgs, "imgs")
     n, c, h, w = imgs.shape
     b = band_halfwidth(h, w, L)
     nb = 2 * b + 1
+    if imgs.dtype == torch.uint8 and not u8_supported(c, h, w, b):
+        imgs = imgs.float()          # device-side conversion; only the static fused kernels read uint8 directly
     if out is None:
         out = torch.empty((n, c, nb, nb), dtype=torch.float32, device=imgs.device)
     else:
@@ -84,6 +102,10 @@ def build_amp_bank(imgs: torch.Tensor, L: float = 0.1, out: torch.Tensor | None 
         if tuple(out.shape) != (n, c, nb, nb):
             raise ValueError("out must have shape %s, got %s" % ((n, c, nb, nb), tuple(out.shape)))
     lib = _lib.load()
+    if imgs.dtype == torch.uint8:
+        with torch.cuda.device(imgs.device):
+            _lib.check(lib.ramdsir_bank_build_u8(imgs.data_ptr(), out.data_ptr(), n, c, h, w, b, _stream_ptr(stream)))
+        return out
     with torch.cuda.device(imgs.device):
         ws, ws_ptr, ws_n = _workspace(workspace_bytes(n, c, h, w, b), imgs.device, workspace)
         _lib.check(lib.ramdsir_bank_build_f32(imgs.data_ptr(), out.data_ptr(), n, c, h, w, b, ws_ptr, ws_n,
@@ -113,7 +135,8 @@ def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L
                   clean_out: torch.Tensor | None = None) -> torch.Tensor:
     """Random Amplitude Mixup of a batch (K1/K2).
 
-    src [B, C, H, W] float32 CUDA; bank [N, C, 2b+1, 2b+1] from `build_amp_bank`;
+    src [B, C, H, W] float32 CUDA, or uint8 (read directly by the kernel on the static shapes, bit-identical to
+    passing src.float(); converted on the device otherwise); bank [N, C, 2b+1, 2b+1] from `build_amp_bank`;
     partner_idx [B] int (indices into the bank); ratio_k [B] int, ratio = ratio_k / ratio_den is the
     weight of the SOURCE amplitude (fundus.py:35,37; the reference draws ratio_k = randint(1, 10)).
     Returns clamp(RAM(src), clip) * scale + shift, float32 [B, C, H, W].
@@ -125,11 +148,13 @@ def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L
     the stream produced (back-to-back batches with their own buffers); the launch may then overlap the tail
     of the previous RAM launch (RAMDSIR_FLAG_INDEPENDENT in include/ramdsir.h).
     """
-    src = _need_cuda_f32(src, "src", 4)
+    src = _need_cuda_src(src, "src")
     bank = _need_cuda_f32(bank, "bank", 4)
     bsz, c, h, w = src.shape
     b = band_halfwidth(h, w, L)
     nb = 2 * b + 1
+    if src.dtype == torch.uint8 and not u8_supported(c, h, w, b):
+        src = src.float()
     if tuple(bank.shape[1:]) != (c, nb, nb):
         raise ValueError("bank must be [N, %d, %d, %d] for src %s and L=%g, got %s"
                          % (c, nb, nb, tuple(src.shape), L, tuple(bank.shape)))
@@ -137,7 +162,7 @@ def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L
         raise ValueError("src and bank must live on the same device")
     n_bank = bank.shape[0]
     if out is None:
-        out = torch.empty_like(src)
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
     else:
         _need_cuda_f32(out, "out", 4)
         if out.shape != src.shape or out.data_ptr() == src.data_ptr():
@@ -151,6 +176,17 @@ def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L
     if pidx.numel() != bsz or rk.numel() != bsz:
         raise ValueError("partner_idx and ratio_k must have one entry per image")
     lib = _lib.load()
+    if src.dtype == torch.uint8:
+        with torch.cuda.device(src.device):
+            _lib.check(lib.ramdsir_mix_dual_u8(src.data_ptr(), bank.data_ptr(), pidx.data_ptr(), rk.data_ptr(),
+                                               out.data_ptr(), None if clean_out is None else clean_out.data_ptr(),
+                                               bsz, c, h, w, b, n_bank, int(ratio_den),
+                                               float(clip[0]), float(clip[1]), float(scale), float(shift),
+                                               _stream_ptr(stream), _lib.FLAG_INDEPENDENT if independent else 0))
+            cur = torch.cuda.current_stream() if stream is None else stream
+            pidx.record_stream(cur)
+            rk.record_stream(cur)
+        return out
     with torch.cuda.device(src.device):
         ws, ws_ptr, ws_n = _workspace(workspace_bytes(bsz, c, h, w, b), src.device, workspace)
         _lib.check(lib.ramdsir_mix_dual_f32(src.data_ptr(), bank.data_ptr(), pidx.data_ptr(), rk.data_ptr(),

@@ -89,6 +89,23 @@ __device__ __forceinline__ float4 ldg_policy(const float4* p, unsigned long long
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
   return v;
 }
+// uint8 sources (images straight from the decoder, fundus.py:205-214 hands RAM uint8-valued pixels): one 32-bit load
+// is four adjacent pixels.  Byte -> float through the 2^23 trick (PRMT + FADD, exact; no quarter-rate I2F).
+__device__ __forceinline__ float4 quad_of_bytes(unsigned v) {
+  const float m = 8388608.f;
+  return make_float4(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7541)) - m,
+                     __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7542)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7543)) - m);
+}
+__device__ __forceinline__ float4 ldg_policy(const unsigned* p, unsigned long long pol) {
+  unsigned v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return quad_of_bytes(v);
+}
+__device__ __forceinline__ float4 ldg_plain(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float4 ldg_plain(const unsigned* p) { return quad_of_bytes(__ldg(p)); }
+template <class T> struct QuadOf;                                   // the 4-pixel load unit of a source type
+template <> struct QuadOf<float> { using type = float4; };
+template <> struct QuadOf<unsigned char> { using type = unsigned; };
 __device__ __forceinline__ void stg_policy(float4* p, float4 v, unsigned long long pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
@@ -106,9 +123,20 @@ __device__ __forceinline__ void prefetch_strip(const float4* x4, int strip, int 
   prefetch_l2(p + 8);
 }
 
-template <class CFG, bool BANK, bool DUAL>
+// uint8 planes: a strip is 64 bytes per row, so two neighbouring strips share each 128-byte line.  Prefetch one line
+// per row when the walk enters a new line (ascending: even strips; descending: odd strips).
+template <class CFG>
+__device__ __forceinline__ void prefetch_strip(const unsigned* x4, int strip, int tid, bool descending = false) {
+  if (((strip & 1) != 0) != descending) return;
+  for (int row = tid; row < CFG::H; row += CFG::nthreads)
+    prefetch_l2(reinterpret_cast<const char*>(x4 + (size_t)row * CFG::M) + (strip >> 1) * 128);
+}
+template <class CFG>
+__device__ __forceinline__ void prefetch_strip(const float4* x4, int strip, int tid, bool) { prefetch_strip<CFG>(x4, strip, tid); }
+
+template <class CFG, bool BANK, bool DUAL, class TIn = float>
 __global__ void __launch_bounds__(CFG::nthreads, (CFG::smemBytes <= 113 * 1024) ? 2 : 1)
-ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__ bank,
+ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ bank,
                         const int64_t* __restrict__ pidx, const int32_t* __restrict__ rk, int ratio_den, int n_bank,
                         int C, float* __restrict__ out, const Epilogue ep, const float* __restrict__ tables, int nplanes,
                         float* __restrict__ clean) {
@@ -129,8 +157,9 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
   constexpr size_t plane_px = (size_t)CFG::H * CFG::W;
   constexpr size_t patch_px = (size_t)CFG::nb * CFG::nb;
   for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
-    const float4* x4 = reinterpret_cast<const float4*>(src + plane * plane_px);
-    auto ld_first = [&](size_t off) { return BANK ? __ldg(x4 + off) : ldg_policy(x4 + off, pol_keep); };
+    using Quad = typename QuadOf<TIn>::type;
+    const Quad* x4 = reinterpret_cast<const Quad*>(src + plane * plane_px);
+    auto ld_first = [&](size_t off) { return BANK ? ldg_plain(x4 + off) : ldg_policy(x4 + off, pol_keep); };
     Epilogue epp = ep;
     float omr = 0.f;
     const float* patch = nullptr;
@@ -233,8 +262,8 @@ ram_fused_static_kernel(const float* __restrict__ src, const float* __restrict__
       const int next = plane + gridDim.x;
       for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
         cf eva[8], evb[8], oda[8], odb[8];
-        if (strip > 0) prefetch_strip<CFG>(x4, strip - 1, tid);
-        else if (next < nplanes) prefetch_strip<CFG>(reinterpret_cast<const float4*>(src + next * plane_px), 0, tid);
+        if (strip > 0) prefetch_strip<CFG>(x4, strip - 1, tid, true);
+        else if (next < nplanes) prefetch_strip<CFG>(reinterpret_cast<const Quad*>(src + next * plane_px), 0, tid);
         for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 0, u);
         __syncthreads();
         s_inv_fft8<CFG>(sm, tid, 0, eva, evb);
@@ -560,31 +589,32 @@ int launch(const FusedPlan& p, const float* src, const float* bank, const int64_
   return RAMDSIR_OK;
 }
 
-template <class CFG, bool BANK>
+template <class CFG, bool BANK, class TIn = float>
 struct KernelOf {
   static constexpr bool dual = true;    // takes the extra `clean` pointer; a second instantiation writes it
-  static auto get() { return ram_fused_static_kernel<CFG, BANK, false>; }
-  static auto get_dual() { return ram_fused_static_kernel<CFG, BANK, !BANK>; }
+  static auto get() { return ram_fused_static_kernel<CFG, BANK, false, TIn>; }
+  static auto get_dual() { return ram_fused_static_kernel<CFG, BANK, !BANK, TIn>; }
 };
 template <int H, int W, int B, bool BANK>
-struct KernelOf<PCfg<H, W, B>, BANK> {
+struct KernelOf<PCfg<H, W, B>, BANK, float> {
   static constexpr bool dual = false;
   static auto get() { return ram_fused_p2_kernel<PCfg<H, W, B>, BANK>; }
 };
 
 template <int H, int W, int B, bool BANK>
-struct KernelOf<XCfg<H, W, B>, BANK> {
+struct KernelOf<XCfg<H, W, B>, BANK, float> {
   static constexpr bool dual = true;
   static auto get() { return ram_fused_x2_kernel<XCfg<H, W, B>, BANK, false>; }
   static auto get_dual() { return ram_fused_x2_kernel<XCfg<H, W, B>, BANK, !BANK>; }
 };
 
-template <class CFG, bool BANK>
-int launch_static(const FusedPlan& p, const float* src, const float* bank, const int64_t* pidx, const int32_t* rk,
+template <class CFG, bool BANK, class TIn = float>
+int launch_static(const FusedPlan& p, const TIn* src, const float* bank, const int64_t* pidx, const int32_t* rk,
                   int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
-  auto kern = KernelOf<CFG, BANK>::get();
-  if constexpr (KernelOf<CFG, BANK>::dual) {
-    if (t_clean && !BANK) kern = KernelOf<CFG, BANK>::get_dual();
+  using KO = KernelOf<CFG, BANK, TIn>;
+  auto kern = KO::get();
+  if constexpr (KO::dual) {
+    if (t_clean && !BANK) kern = KO::get_dual();
   }
   // cudaFuncSetAttribute and occupancy are per device: cache per (instantiation, device)
   static thread_local int per_sm_dev[64] = {0};
@@ -592,9 +622,9 @@ int launch_static(const FusedPlan& p, const float* src, const float* bank, const
   RD_CUDA(cudaGetDevice(&dev));
   int& per_sm = per_sm_dev[dev & 63];
   if (per_sm == 0) {
-    RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
-    if constexpr (KernelOf<CFG, BANK>::dual)
-      RD_CUDA(cudaFuncSetAttribute(KernelOf<CFG, BANK>::get_dual(), cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
+    RD_CUDA(cudaFuncSetAttribute(KO::get(), cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
+    if constexpr (KO::dual)   // whichever of the two instantiations this first call uses, configure both
+      RD_CUDA(cudaFuncSetAttribute(KO::get_dual(), cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
     RD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::nthreads, CFG::smemBytes));
     if (per_sm < 1) per_sm = 1;
   }
@@ -612,12 +642,12 @@ int launch_static(const FusedPlan& p, const float* src, const float* bank, const
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if constexpr (KernelOf<CFG, BANK>::dual)
+    if constexpr (KO::dual)
       RD_CUDA(cudaLaunchKernelEx(&cfg, kern, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, (const float*)p.tables, nplanes, t_clean));
     else
       RD_CUDA(cudaLaunchKernelEx(&cfg, kern, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, (const float*)p.tables, nplanes));
   } else {
-    if constexpr (KernelOf<CFG, BANK>::dual)
+    if constexpr (KO::dual)
       kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes, BANK ? nullptr : t_clean);
     else
       kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes);
@@ -646,7 +676,37 @@ int dispatch(const FusedPlan& p, const float* src, const float* bank, const int6
   set_error("band half-width %d too large for the fused path", p.S.b);
   return RAMDSIR_ERR_UNSUPPORTED;
 }
+
+template <bool BANK>
+int dispatch_u8(const FusedPlan& p, const unsigned char* src, const float* bank, const int64_t* pidx, const int32_t* rk,
+                int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
+  if (p.static_id == 1) return launch_static<Cfg256, BANK, unsigned char>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
+  if (p.static_id == 2) return launch_static<Cfg384, BANK, unsigned char>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
+  set_error("uint8 sources are read directly only by the static fused kernels (256x256/b=25, 384x384/b=38)");
+  return RAMDSIR_ERR_UNSUPPORTED;
+}
 }  // namespace
+
+bool fused_u8_supported(int H, int W, int b) {
+  const int id = static_id_of(H, W, b, g_variant.load(std::memory_order_relaxed));
+  return id == 1 || id == 2;
+}
+
+int fused_mix_u8(const MixArgs& a, const unsigned char* src, cudaStream_t st) {
+  FusedPlan* p = nullptr;
+  int rc = get_plan(a.H, a.W, a.b, &p);
+  if (rc) return rc;
+  t_overlap = a.independent ? 1 : 0;
+  t_clean = a.clean;
+  return dispatch_u8<false>(*p, src, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, a.out, a.ep, a.B * a.C, st);
+}
+
+int fused_bank_u8(const unsigned char* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st) {
+  FusedPlan* p = nullptr;
+  int rc = get_plan(H, W, b, &p);
+  if (rc) return rc;
+  return dispatch_u8<true>(*p, imgs, nullptr, nullptr, nullptr, 10, 0, C, bank, Epilogue{0, 0, 1, 0}, N * C, st);
+}
 
 bool fused_dual_supported(int H, int W, int b) {
   const int id = static_id_of(H, W, b, g_variant.load(std::memory_order_relaxed));

@@ -39,6 +39,10 @@ int u8_to_f32(const unsigned char* x, float* y, size_t n, cudaStream_t st);
 int affine_f32(const float* x, float* y, size_t n, float scale, float shift, cudaStream_t st);
 int fused_mix(const MixArgs& a, cudaStream_t st);
 int fused_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st);
+// uint8 sources read directly by the static fused kernels (a.src is ignored)
+bool fused_u8_supported(int H, int W, int b);
+int fused_mix_u8(const MixArgs& a, const unsigned char* src, cudaStream_t st);
+int fused_bank_u8(const unsigned char* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st);
 
 // multi-pass path for large planes (ram_multipass.cu)
 bool multipass_supported(int H, int W, int b);

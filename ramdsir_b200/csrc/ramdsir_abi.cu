@@ -185,6 +185,60 @@ int ramdsir_mix_dual_f32(const float* src_dev, const float* bank_dev, const int6
   return RAMDSIR_ERR_UNSUPPORTED;
 }
 
+int ramdsir_u8_supported(int C, int H, int W, int b) {
+  if (check_shape(0, C, H, W, b)) return 0;
+  return (path_of(H, W, b) == RAMDSIR_PATH_FUSED && fused_u8_supported(H, W, b)) ? 1 : 0;
+}
+
+int ramdsir_bank_build_u8(const uint8_t* imgs_dev, float* bank_dev, int N, int C, int H, int W, int b, void* stream) {
+  int rc = check_shape(N, C, H, W, b);
+  if (rc) return rc;
+  if (N == 0) return RAMDSIR_OK;
+  if (!imgs_dev || !bank_dev || (reinterpret_cast<uintptr_t>(imgs_dev) & 3u)) {
+    set_error("bank_build_u8: null or misaligned pointer (imgs must be 4-byte aligned)");
+    return RAMDSIR_ERR_INVALID;
+  }
+  if (!ramdsir_u8_supported(C, H, W, b)) {
+    set_error("bank_build_u8: uint8 sources are read directly only at 256x256/b=25 and 384x384/b=38 (got H=%d W=%d b=%d)", H, W, b);
+    return RAMDSIR_ERR_UNSUPPORTED;
+  }
+  return fused_bank_u8(imgs_dev, bank_dev, N, C, H, W, b, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ramdsir_mix_dual_u8(const uint8_t* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
+                        const int32_t* ratio_k_dev, float* out_dev, float* clean_out_dev, int B, int C, int H, int W,
+                        int b, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
+                        void* stream, unsigned flags) {
+  int rc = check_shape(B, C, H, W, b);
+  if (rc) return rc;
+  if (B == 0) return RAMDSIR_OK;
+  if (!src_dev || !bank_dev || !partner_idx_dev || !ratio_k_dev || !out_dev) {
+    set_error("mix_u8: null pointer");
+    return RAMDSIR_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(src_dev) & 3u) || !aligned16(out_dev) || (clean_out_dev && !aligned16(clean_out_dev))) {
+    set_error("mix_u8: src must be 4-byte aligned, out and clean_out 16-byte aligned");
+    return RAMDSIR_ERR_INVALID;
+  }
+  if (n_bank < 1 || ratio_den < 1) {
+    set_error("mix_u8: n_bank=%d ratio_den=%d must be positive", n_bank, ratio_den);
+    return RAMDSIR_ERR_INVALID;
+  }
+  if (clean_out_dev && clean_out_dev == out_dev) {
+    set_error("mix_u8: clean_out must be distinct from out");
+    return RAMDSIR_ERR_INVALID;
+  }
+  if (!ramdsir_u8_supported(C, H, W, b)) {
+    set_error("mix_u8: uint8 sources are read directly only at 256x256/b=25 and 384x384/b=38 (got H=%d W=%d b=%d)", H, W, b);
+    return RAMDSIR_ERR_UNSUPPORTED;
+  }
+  MixArgs a{nullptr, bank_dev, partner_idx_dev, ratio_k_dev, out_dev, B, C, H, W, b, n_bank, ratio_den,
+            Epilogue{clip_lo, clip_hi, scale, shift}};
+  a.independent = (flags & RAMDSIR_FLAG_INDEPENDENT) != 0;
+  a.clean = clean_out_dev;
+  return fused_mix_u8(a, src_dev, reinterpret_cast<cudaStream_t>(stream));
+}
+
 size_t ramdsir_amp_spectrum_workspace_bytes(int N, int C, int H, int W) {
   if (N < 0 || C < 1 || H < 1 || W < 1) return 0;
   return full_amp_workspace_bytes(N, C, H, W);
@@ -303,18 +357,25 @@ static int mix_host_impl(ramdsir_pipe_t* p, const float* src_host, const unsigne
     const int n = (B - i0 < p->chunk) ? B - i0 : p->chunk;
     cudaStream_t st = p->st[slot];
     const size_t off = (size_t)i0 * p->img_elems, bytes = (size_t)n * p->img_elems * sizeof(float);
-    if (src_u8_host) {   // uint8 ingestion: a quarter of the H2D bytes, widened on the device
-      if (!p->d_u8[slot]) RD_CUDA(cudaMalloc(&p->d_u8[slot], p->img_elems * (size_t)p->chunk));
-      RD_CUDA(cudaMemcpyAsync(p->d_u8[slot], src_u8_host + off, (size_t)n * p->img_elems, cudaMemcpyHostToDevice, st));
-      int rcu = u8_to_f32(p->d_u8[slot], p->d_src[slot], (size_t)n * p->img_elems, st);
-      if (rcu) return rcu;
-    } else {
-      RD_CUDA(cudaMemcpyAsync(p->d_src[slot], src_host + off, bytes, cudaMemcpyHostToDevice, st));
-    }
     RD_CUDA(cudaMemcpyAsync(p->d_pidx[slot], partner_idx_host + i0, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
     RD_CUDA(cudaMemcpyAsync(p->d_rk[slot], ratio_k_host + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-    int rc = ramdsir_mix_f32(p->d_src[slot], bank_dev, p->d_pidx[slot], p->d_rk[slot], p->d_out[slot], n, p->C, p->H,
-                             p->W, p->b, n_bank, ratio_den, clip_lo, clip_hi, scale, shift, p->d_ws[slot], p->ws_bytes, st);
+    int rc;
+    if (src_u8_host) {   // uint8 ingestion: a quarter of the H2D bytes
+      if (!p->d_u8[slot]) RD_CUDA(cudaMalloc(&p->d_u8[slot], p->img_elems * (size_t)p->chunk));
+      RD_CUDA(cudaMemcpyAsync(p->d_u8[slot], src_u8_host + off, (size_t)n * p->img_elems, cudaMemcpyHostToDevice, st));
+      if (ramdsir_u8_supported(p->C, p->H, p->W, p->b)) {   // the RAM kernel reads the bytes itself
+        rc = ramdsir_mix_dual_u8(p->d_u8[slot], bank_dev, p->d_pidx[slot], p->d_rk[slot], p->d_out[slot], nullptr, n, p->C,
+                                 p->H, p->W, p->b, n_bank, ratio_den, clip_lo, clip_hi, scale, shift, st, 0u);
+      } else {                                              // widened on the device first
+        rc = u8_to_f32(p->d_u8[slot], p->d_src[slot], (size_t)n * p->img_elems, st);
+        if (!rc) rc = ramdsir_mix_f32(p->d_src[slot], bank_dev, p->d_pidx[slot], p->d_rk[slot], p->d_out[slot], n, p->C, p->H,
+                                      p->W, p->b, n_bank, ratio_den, clip_lo, clip_hi, scale, shift, p->d_ws[slot], p->ws_bytes, st);
+      }
+    } else {
+      RD_CUDA(cudaMemcpyAsync(p->d_src[slot], src_host + off, bytes, cudaMemcpyHostToDevice, st));
+      rc = ramdsir_mix_f32(p->d_src[slot], bank_dev, p->d_pidx[slot], p->d_rk[slot], p->d_out[slot], n, p->C, p->H,
+                           p->W, p->b, n_bank, ratio_den, clip_lo, clip_hi, scale, shift, p->d_ws[slot], p->ws_bytes, st);
+    }
     if (rc) return rc;
     RD_CUDA(cudaMemcpyAsync(out_host + off, p->d_out[slot], bytes, cudaMemcpyDeviceToHost, st));
   }

@@ -119,11 +119,17 @@ class Fundus_Multi(_MultiBase):
             other_lines = f.readlines()
         other_id = np.random.choice(other_lines).replace("\n", "").split(" ")[0]
         other = Image.open(os.path.join(self.base_dir, other_domain, other_id)).resize((256, 256), Image.BILINEAR)
-        other = np.array(other).astype(np.float32).transpose(2, 0, 1)
-        src = np.array(img).astype(np.float32).transpose(2, 0, 1)
+        other_u8, src_u8 = np.array(other), np.array(img)
+        other = other_u8.astype(np.float32).transpose(2, 0, 1)
+        src = src_u8.astype(np.float32).transpose(2, 0, 1)
         ratio_k = random.randint(1, 10)                          # fundus.py:35 (drawn inside low_freq_mutate_np)
         mask_t = encode_fundus_mask(mask)
         if self.ram == "deferred":
+            if src_u8.dtype == np.uint8 and other_u8.dtype == np.uint8:
+                # 8-bit images stay 8-bit until the RAM kernel reads them: a quarter of the bytes through the
+                # worker queue and over PCIe; the kernel's float(src) is the reference's astype(float32)
+                return (torch.from_numpy(np.ascontiguousarray(src_u8.transpose(2, 0, 1))),
+                        torch.from_numpy(np.ascontiguousarray(other_u8.transpose(2, 0, 1))), ratio_k, mask_t)
             return torch.from_numpy(src), torch.from_numpy(other), ratio_k, mask_t
         img_freq = _gpu_ram_one(src, other, ratio_k, FUNDUS_EPILOGUE)           # fundus.py:213-215,222-225
         img_t = torch.from_numpy(_normalise_u8(src))                            # fundus.py:217-220
@@ -191,15 +197,19 @@ class RamBatchHook:
 
     def __call__(self, batch):
         img_raw, partner, ratio_k, mask = batch
-        img_raw = img_raw.to(self.device, non_blocking=True).float().contiguous()
-        partner = partner.to(self.device, non_blocking=True).float().contiguous()
+        img_raw = img_raw.to(self.device, non_blocking=True).contiguous()
+        partner = partner.to(self.device, non_blocking=True).contiguous()
+        if img_raw.dtype != torch.uint8:
+            img_raw = img_raw.float()
+        if partner.dtype != torch.uint8:
+            partner = partner.float()
         bank = build_amp_bank(partner, L=self.L)                 # row i is sample i's partner
         idx = torch.arange(img_raw.shape[0], device=self.device)
         lo, hi, scale, shift = FUNDUS_EPILOGUE if self.dataset == "fundus" else PROSTATE_EPILOGUE
         # fundus: the kernel also emits the normalised clean batch from the same read of img_raw (fused dual output)
-        img = torch.empty_like(img_raw) if self.dataset == "fundus" else None
+        img = torch.empty(img_raw.shape, dtype=torch.float32, device=self.device) if self.dataset == "fundus" else None
         img_freq = ram_mix_batch(img_raw, bank, idx, torch.as_tensor(ratio_k, dtype=torch.int32), L=self.L,
                                  clip=(lo, hi), scale=scale, shift=shift, clean_out=img)
         if img is None:
-            img = img_raw                                         # prostate.py:190-193: the clean image is untouched
+            img = img_raw.float()                                 # prostate.py:190-193: the clean image is untouched
         return img, img_freq, mask.to(self.device, non_blocking=True)

@@ -28,7 +28,8 @@ def test_fundus_host_side_matches_reference(golden, tmp_path, tag, out_domain):
         after = np.array([random.random(), np.random.rand()])
         key = "fundus_%s_%d" % (tag, i)
         np.testing.assert_array_equal(after, golden[key + "_after"])       # identical RNG consumption
-        img = img_raw.numpy().copy()
+        assert img_raw.dtype == partner.dtype == __import__("torch").uint8    # 8-bit images travel as bytes
+        img = img_raw.numpy().astype(np.float32)
         img /= 127.5
         img -= 1.0
         np.testing.assert_array_equal(img[:, ::8, ::8], golden[key + "_img"])

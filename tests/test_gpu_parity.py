@@ -437,3 +437,77 @@ def test_host_pipeline_matches_device_path(R):
         assert torch.equal(out_u8, want)
     empty = torch.empty(0, C, H, W, device="cuda")
     assert R.ram_mix_batch(empty, bank, [], []).shape == (0, C, H, W)
+
+
+# ------------------------------------------------------------------ uint8 sources (ramdsir_mix_dual_u8 / bank_build_u8)
+@pytest.mark.parametrize("shape", [(3, 256, 256), (1, 384, 384), (3, 384, 384)], ids=["fundus", "prostate1", "prostate3"])
+@pytest.mark.parametrize("independent", [False, True])
+def test_uint8_sources_are_bit_identical_to_float(R, shape, independent):
+    """The kernels that read uint8 planes directly compute on float(src): bank, img_freq and the fused clean
+    output are bit-identical to the float32 entry points on the converted input (fundus.py:205-214 astype)."""
+    c, h, w = shape
+    assert R.api.u8_supported(c, h, w, R.band_halfwidth(h, w))
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, N = 301, 7                                           # more planes than CTAs, ragged
+    src = torch.randint(0, 256, (B, c, h, w), device="cuda", generator=g, dtype=torch.uint8)
+    partners = torch.randint(0, 256, (N, c, h, w), device="cuda", generator=g, dtype=torch.uint8)
+    src[5] = 0                                              # all-zero and constant planes (phase-0 convention)
+    src[6] = 255
+    bank_u8 = R.build_amp_bank(partners)
+    bank_f = R.build_amp_bank(partners.float())
+    assert torch.equal(bank_u8, bank_f)
+    rs = np.random.RandomState(5)
+    pidx, rk = rs.randint(0, N, B), rs.randint(1, 11, B)
+    kw = dict(clip=(0.0, 255.0), scale=1 / 127.5, shift=-1.0, independent=independent)
+    want_clean = torch.empty((B, c, h, w), device="cuda")
+    want = R.ram_mix_batch(src.float(), bank_f, pidx, rk, clean_out=want_clean, **kw)
+    got_clean = torch.empty_like(want_clean)
+    got = R.ram_mix_batch(src, bank_u8, pidx, rk, clean_out=got_clean, **kw)
+    assert got.dtype == torch.float32 and torch.equal(got, want) and torch.equal(got_clean, want_clean)
+    assert torch.equal(R.ram_mix_batch(src, bank_u8, pidx, rk, **kw), want)       # single-output instantiation
+    # offsets that are only 4-byte aligned in the uint8 buffer (a view starting at image 1 of a C=1 batch is fine;
+    # here: an odd number of leading bytes is refused, never mis-read)
+    from ramdsir_b200 import _lib
+    lib = _lib.load()
+    idx1 = torch.zeros(1, dtype=torch.int64, device="cuda")
+    rk1 = torch.ones(1, dtype=torch.int32, device="cuda")
+    rc = lib.ramdsir_mix_dual_u8(src.data_ptr() + 1, bank_u8.data_ptr(), idx1.data_ptr(), rk1.data_ptr(), got.data_ptr(),
+                                 None, 1, c, h, w, R.band_halfwidth(h, w), N, 10, 0.0, 255.0, 1.0, 0.0, None, 0)
+    assert rc == _lib.ERR_INVALID and b"aligned" in lib.ramdsir_last_error()
+
+
+def test_uint8_golden_fundus(R, golden_dir):
+    """The reference's own fundus sample (uint8 pixels) through the uint8 entry points."""
+    g = np.load(os.path.join(golden_dir, "ram_fundus256.npz"))
+    L, k = g["meta"]
+    assert g["src"].dtype == np.uint8
+    src, trg = torch.from_numpy(g["src"][None]).cuda(), torch.from_numpy(g["trg"][None]).cuda()
+    bank = R.build_amp_bank(trg, L=float(L))
+    lo, hi, sc, sh = O.FUNDUS_EPILOGUE
+    got = R.ram_mix_batch(src, bank, [0], [int(k)], L=float(L), clip=(lo, hi), scale=sc, shift=sh).cpu().numpy()
+    check(got[0], O.epilogue(g["out_f64"].transpose(2, 0, 1), *O.FUNDUS_EPILOGUE), "fundus256 uint8")
+
+
+def test_uint8_sources_other_shapes_convert_on_device(R):
+    """Shapes without a uint8-reading kernel: the C ABI refuses (no silent slow path), the Python API widens on the
+    device and takes the float32 path."""
+    from ramdsir_b200 import _lib
+    lib = _lib.load()
+    c, h, w = 2, 64, 128
+    b = R.band_halfwidth(h, w)
+    assert not R.api.u8_supported(c, h, w, b)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    src = torch.randint(0, 256, (4, c, h, w), device="cuda", generator=g, dtype=torch.uint8)
+    bank = R.build_amp_bank(src[:2])
+    assert torch.equal(bank, R.build_amp_bank(src[:2].float()))
+    out = torch.empty((4, c, h, w), device="cuda")
+    rc = lib.ramdsir_mix_dual_u8(src.data_ptr(), bank.data_ptr(), 0, 0, out.data_ptr(), None, 4, c, h, w, b, 2, 10,
+                                 0.0, 255.0, 1.0, 0.0, None, 0)
+    assert rc == _lib.ERR_INVALID          # null index pointers are checked first
+    idx = torch.zeros(4, dtype=torch.int64, device="cuda")
+    rk = torch.ones(4, dtype=torch.int32, device="cuda")
+    rc = lib.ramdsir_mix_dual_u8(src.data_ptr(), bank.data_ptr(), idx.data_ptr(), rk.data_ptr(), out.data_ptr(), None,
+                                 4, c, h, w, b, 2, 10, 0.0, 255.0, 1.0, 0.0, None, 0)
+    assert rc == _lib.ERR_UNSUPPORTED and b"uint8" in lib.ramdsir_last_error()
+    assert torch.equal(R.ram_mix_batch(src, bank, [0, 1, 0, 1], [1, 4, 7, 10]),
+                       R.ram_mix_batch(src.float(), bank, [0, 1, 0, 1], [1, 4, 7, 10]))
