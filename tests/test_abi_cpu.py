@@ -73,6 +73,34 @@ def test_invalid_arguments_return_codes_not_crashes(lib):
     assert lib.ramdsir_force_path(7) == _lib.ERR_INVALID
 
 
+def test_uint8_entry_points_validate_without_gpu(lib):
+    """ramdsir_u8_supported is pure host logic; the uint8 entry points refuse bad arguments before touching CUDA."""
+    from ramdsir_b200 import _lib
+    assert lib.ramdsir_u8_supported(3, 256, 256, 25) == 1
+    assert lib.ramdsir_u8_supported(1, 384, 384, 38) == 1
+    assert lib.ramdsir_u8_supported(3, 256, 256, 20) == 0        # runtime-shape fused kernel: float32 only
+    assert lib.ramdsir_u8_supported(3, 1024, 1024, 102) == 0     # multipass
+    assert lib.ramdsir_u8_supported(2, 31, 45, 3) == 0           # generic
+    args = (4, 3, 256, 256, 25, 1, 10, 0.0, 255.0, 1.0, 0.0, None, 0)
+    assert lib.ramdsir_mix_dual_u8(None, None, None, None, None, None, *args) == _lib.ERR_INVALID
+    assert b"null" in lib.ramdsir_last_error()
+    assert lib.ramdsir_mix_dual_u8(6, 16, 16, 16, 32, None, *args) == _lib.ERR_INVALID      # src not 4-byte aligned
+    assert b"aligned" in lib.ramdsir_last_error()
+    assert lib.ramdsir_mix_dual_u8(8, 16, 16, 16, 32, 32, *args) == _lib.ERR_INVALID        # clean_out aliases out
+    rc = lib.ramdsir_mix_dual_u8(8, 16, 16, 16, 32, None, 4, 3, 128, 128, 12, 1, 10, 0.0, 255.0, 1.0, 0.0, None, 0)
+    assert rc == _lib.ERR_UNSUPPORTED and b"uint8" in lib.ramdsir_last_error()
+    assert lib.ramdsir_bank_build_u8(8, 16, 2, 3, 128, 128, 12, None) == _lib.ERR_UNSUPPORTED
+    assert lib.ramdsir_bank_build_u8(None, None, 0, 3, 256, 256, 25, None) == _lib.OK       # empty batch
+
+
+def test_uint8_to_float_trick_is_exact():
+    """quad_of_bytes (ram_fused.cu): float(0x4B000000 | byte) - 2^23 == byte for every byte value."""
+    import numpy as np
+    b = np.arange(256, dtype=np.uint32)
+    f = (np.uint32(0x4B000000) | b).view(np.float32) - np.float32(8388608.0)
+    assert f.dtype == np.float32 and np.array_equal(f, b.astype(np.float32))
+
+
 def test_product_path_refuses_cpu_tensors():
     import torch
     import ramdsir_b200 as R
