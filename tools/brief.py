@@ -1,5 +1,5 @@
-import sys, json
-for ln in sys.stdin:
+import sys, json, fileinput
+for ln in fileinput.input():      # files given as arguments, else stdin
     ln = ln.strip()
     if not ln.startswith("{"): continue
     d = json.loads(ln)
