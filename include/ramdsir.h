@@ -64,38 +64,52 @@ int ramdsir_band_halfwidth(int H, int W, double L);
 /* Which kernel family serves this shape (RAMDSIR_PATH_*). */
 int ramdsir_path(int C, int H, int W, int b);
 
-/* Testing knob: route every later call through the generic kernels (RAMDSIR_PATH_GENERIC) so two
- * independent CUDA implementations can be compared; 0 restores automatic selection. */
-int ramdsir_force_path(int path);
+/*
+ * Optional warm-up: builds the per-(device, H, W, b) twiddle tables now instead of on the first call.  Table
+ * construction uploads a few KB on a private stream and synchronises THAT stream only (never the device, never the
+ * caller's streams); call this once per shape outside a latency-critical region if even that matters.
+ */
+int ramdsir_prepare(int C, int H, int W, int b);
 
-/* Tuning/testing knob for the fused path: 0 = auto (float4 static-shape kernels where instantiated),
- * 1 = "P2" static kernels (one packed column per thread, 64 registers), 2 = runtime-shape kernel,
- * 4 = "x2" static kernels (packed f32x2 arithmetic).  All variants compute the same result within tolerance;
- * 0 is the fastest measured. */
-int ramdsir_set_fused_variant(int variant);
+/*
+ * Per-call flags (the `flags` argument of the *_ex / dual entry points).  There is no process-global state.
+ *
+ * Overlap of consecutive launches.  By default the static fused kernels decide by themselves whether a launch may
+ * start on SMs that the previous RAM launch in the same stream has already vacated (programmatic dependent launch):
+ * the library knows every buffer of both launches and overlaps them only if they touch disjoint memory (no
+ * read-after-write, write-after-read or write-after-write between them).  Either way the later launch does not
+ * COMPLETE before the earlier one (griddepcontrol.wait at its end), so ordering against copies, events and every other
+ * kernel in the stream is the plain stream order.
+ *   RAMDSIR_FLAG_INDEPENDENT  skip the check (the caller asserts the buffers are disjoint)
+ *   RAMDSIR_FLAG_SERIAL       never overlap: launch strictly after the previous kernel has finished
+ * Kernel-family selection, for cross-checking two independent CUDA implementations in tests:
+ *   RAMDSIR_FLAG_PATH_GENERIC   use the generic (any-shape, direct band-pruned DFT) kernels
+ *   RAMDSIR_FLAG_RUNTIME_SHAPE  on the fused path, use the runtime-shape kernel even where a static one exists
+ * (Setting the environment variable RAMDSIR_NO_AUTO_OVERLAP=1 before loading the library disables the automatic
+ * decision, leaving only RAMDSIR_FLAG_INDEPENDENT.)
+ */
+#define RAMDSIR_FLAG_INDEPENDENT 1u
+#define RAMDSIR_FLAG_SERIAL 2u
+#define RAMDSIR_FLAG_PATH_GENERIC 4u
+#define RAMDSIR_FLAG_RUNTIME_SHAPE 8u
 
 /* Scratch bytes needed to process `n_images` images of this shape in one call (0 for the fused path). */
 size_t ramdsir_workspace_bytes(int n_images, int C, int H, int W, int b);
+size_t ramdsir_workspace_bytes_ex(int n_images, int C, int H, int W, int b, unsigned flags);
 
 /* K3: amplitude bank.  imgs_dev [N, C, H, W] -> bank_dev [N, C, 2b+1, 2b+1]. */
 int ramdsir_bank_build_f32(const float* imgs_dev, float* bank_dev, int N, int C, int H, int W, int b,
                            void* workspace_dev, size_t workspace_bytes, void* stream);
+int ramdsir_bank_build_f32_ex(const float* imgs_dev, float* bank_dev, int N, int C, int H, int W, int b,
+                              void* workspace_dev, size_t workspace_bytes, void* stream, unsigned flags);
 
-/* K1/K2: RAM.  src_dev [B, C, H, W] -> out_dev [B, C, H, W]; out_dev must not alias src_dev (the source is read twice). */
+/* K1/K2: RAM.  src_dev [B, C, H, W] -> out_dev [B, C, H, W]; out_dev must not overlap src_dev (the source is read twice). */
 int ramdsir_mix_f32(const float* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
                     const int32_t* ratio_k_dev, float* out_dev, int B, int C, int H, int W, int b,
                     int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,
                     void* workspace_dev, size_t workspace_bytes, void* stream);
 
-/*
- * Same as ramdsir_mix_f32 with flags.  RAMDSIR_FLAG_INDEPENDENT: the caller promises that this call does
- * not read or overwrite anything produced by the kernel that precedes it in `stream` (consecutive batches
- * of a loader pipeline, each with its own input and output buffers).  The fused path then launches with
- * programmatic stream serialisation, so this launch starts occupying SMs while the previous RAM launch
- * drains its last wave instead of waiting for it to finish.  Ordering against copies and against every
- * other kernel is unchanged.  Without the flag the call is plainly stream-ordered.
- */
-#define RAMDSIR_FLAG_INDEPENDENT 1u
+/* Same as ramdsir_mix_f32 with RAMDSIR_FLAG_* (see above). */
 int ramdsir_mix_f32_ex(const float* src_dev, const float* bank_dev, const int64_t* partner_idx_dev,
                        const int32_t* ratio_k_dev, float* out_dev, int B, int C, int H, int W, int b,
                        int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift,

@@ -6,10 +6,10 @@ Public surface
   C ABI:                                       include/ramdsir.h -> ramdsir_b200/libramdsir.so
 """
 from .api import (FUNDUS_EPILOGUE, NO_EPILOGUE, PROSTATE_EPILOGUE, band_halfwidth, build_amp_bank, kernel_path,
-                  ram_mix_batch, u8_supported, workspace_bytes)
+                  prepare, ram_mix_batch, u8_supported, workspace_bytes)
 from .freq import extract_amp_spectrum, low_freq_mutate_np, source_to_target_freq
 
 __all__ = ["extract_amp_spectrum", "low_freq_mutate_np", "source_to_target_freq", "build_amp_bank", "u8_supported",
-           "ram_mix_batch", "band_halfwidth", "kernel_path", "workspace_bytes",
+           "ram_mix_batch", "band_halfwidth", "kernel_path", "workspace_bytes", "prepare",
            "FUNDUS_EPILOGUE", "PROSTATE_EPILOGUE", "NO_EPILOGUE"]
 __version__ = "0.1.0"

@@ -16,14 +16,15 @@ LIB_PATH = os.path.join(_HERE, "libramdsir.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["ramdsir_abi.cu", "ram_fused.cu", "ram_generic.cu", "ram_multipass.cu"]
 
-FLAG_INDEPENDENT = 1
+FLAG_INDEPENDENT, FLAG_SERIAL, FLAG_PATH_GENERIC, FLAG_RUNTIME_SHAPE = 1, 2, 4, 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
 PATH_NONE, PATH_FUSED, PATH_MULTIPASS, PATH_GENERIC = 0, 1, 2, 3
 
 # every symbol include/ramdsir.h declares (tests/test_abi_cpu.py checks the .so exports them all)
 SYMBOLS = [
-    "ramdsir_version", "ramdsir_last_error", "ramdsir_band_halfwidth", "ramdsir_path", "ramdsir_force_path", "ramdsir_set_fused_variant",
-    "ramdsir_workspace_bytes", "ramdsir_bank_build_f32", "ramdsir_mix_f32", "ramdsir_mix_f32_ex", "ramdsir_mix_dual_f32",
+    "ramdsir_version", "ramdsir_last_error", "ramdsir_band_halfwidth", "ramdsir_path", "ramdsir_prepare",
+    "ramdsir_workspace_bytes", "ramdsir_workspace_bytes_ex", "ramdsir_bank_build_f32", "ramdsir_bank_build_f32_ex",
+    "ramdsir_mix_f32", "ramdsir_mix_f32_ex", "ramdsir_mix_dual_f32",
     "ramdsir_u8_supported", "ramdsir_bank_build_u8", "ramdsir_mix_dual_u8",
     "ramdsir_amp_spectrum_workspace_bytes", "ramdsir_amp_spectrum_f32", "ramdsir_band_blend_f32",
     "ramdsir_pipe_create", "ramdsir_pipe_destroy", "ramdsir_mix_host_f32", "ramdsir_mix_host_u8", "ramdsir_launch_count",
@@ -67,11 +68,13 @@ def _declare(lib):
     lib.ramdsir_band_halfwidth.argtypes = [c.c_int, c.c_int, c.c_double]
     lib.ramdsir_band_halfwidth.restype = c.c_int
     lib.ramdsir_path.argtypes = [c.c_int] * 4
-    lib.ramdsir_force_path.argtypes = [c.c_int]
-    lib.ramdsir_set_fused_variant.argtypes = [c.c_int]
+    lib.ramdsir_prepare.argtypes = [c.c_int] * 4
     lib.ramdsir_workspace_bytes.argtypes = [c.c_int] * 5
     lib.ramdsir_workspace_bytes.restype = c.c_size_t
+    lib.ramdsir_workspace_bytes_ex.argtypes = [c.c_int] * 5 + [c.c_uint]
+    lib.ramdsir_workspace_bytes_ex.restype = c.c_size_t
     lib.ramdsir_bank_build_f32.argtypes = [vp, vp] + [c.c_int] * 5 + [vp, c.c_size_t, vp]
+    lib.ramdsir_bank_build_f32_ex.argtypes = [vp, vp] + [c.c_int] * 5 + [vp, c.c_size_t, vp, c.c_uint]
     lib.ramdsir_mix_f32.argtypes = ([vp] * 5 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_size_t, vp])
     lib.ramdsir_mix_f32_ex.argtypes = ([vp] * 5 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_size_t, vp, c.c_uint])
     lib.ramdsir_mix_dual_f32.argtypes = ([vp] * 6 + [c.c_int] * 7 + [c.c_float] * 4 + [vp, c.c_size_t, vp, c.c_uint])

@@ -1,7 +1,7 @@
 // Fused RAM kernels for sm_100a: one persistent CTA per image plane, band buffers in shared memory.
 // See ram_fused_core.cuh for the algorithm and the reference lines it follows
 // (/root/reference/code/dataset/fundus.py:13-61).
-#include <atomic>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -83,6 +83,9 @@ ram_fused_kernel(const FusedShape S, const float* __restrict__ src, const float*
 //   * output:      st.global with L2::evict_first    -> streaming stores must not displace x
 //   * the second pass walks the column strips in REVERSE order (most recently read strip first)
 //   * while a strip is being processed, the next strip's lines are prefetched into L2.
+// The twiddle tables (once per CTA) and the partner's amplitude patch (once per plane, issued before the
+// forward columns, consumed after them) arrive by bulk-async copies (cp.async.bulk, the non-tensor TMA
+// path) that signal an mbarrier: no thread holds patch values in registers across the column passes.
 __device__ __forceinline__ float4 ldg_policy(const float4* p, unsigned long long pol) {
   float4 v;
   asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
@@ -112,6 +115,31 @@ __device__ __forceinline__ void stg_policy(float4* p, float4 v, unsigned long lo
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
+// ---- mbarrier + bulk-async copy (cp.async.bulk global -> shared, completion counted in bytes) ---------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" :: "r"(bar), "r"(parity) : "memory");
+}
+
 // Each thread prefetches 2 of the 128-byte lines its warp will load for column strip `strip`:
 // a warp covers rows (h1w + (lane >> 4)) + N1h * (lane & 15), 256 bytes (2 lines) each.
 template <class CFG>
@@ -134,45 +162,63 @@ __device__ __forceinline__ void prefetch_strip(const unsigned* x4, int strip, in
 template <class CFG>
 __device__ __forceinline__ void prefetch_strip(const float4* x4, int strip, int tid, bool) { prefetch_strip<CFG>(x4, strip, tid); }
 
-template <class CFG, bool BANK, bool DUAL, class TIn = float>
+__device__ __forceinline__ EpiClamp poisoned(EpiClamp e) { e.scale = __int_as_float(0x7fc00000); return e; }
+__device__ __forceinline__ EpiSat poisoned(EpiSat e) { e.m = __int_as_float(0x7fc00000); return e; }   // sat() would swallow a NaN
+
+// Per-launch scalars that are not part of the epilogue policy.
+struct MixScalars {
+  int ratio_den, n_bank, C, nplanes;
+  float dscale;    // EpiSat: 1 / (hi - lo), folded into dF;  EpiClamp: 1
+  float dc_add;    // EpiSat: -lo / (hi - lo), added to the DC bin of dF / (H W);  EpiClamp: 0
+  float cscale, cshift;   // fused dual output: clean = x * cscale + cshift
+};
+
+template <class CFG, bool BANK, bool DUAL, class TIn, class EPI>
 __global__ void __launch_bounds__(CFG::nthreads, (CFG::smemBytes <= 113 * 1024) ? 2 : 1)
 ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ bank,
-                        const int64_t* __restrict__ pidx, const int32_t* __restrict__ rk, int ratio_den, int n_bank,
-                        int C, float* __restrict__ out, const Epilogue ep, const float* __restrict__ tables, int nplanes,
+                        const int64_t* __restrict__ pidx, const int32_t* __restrict__ rk,
+                        float* __restrict__ out, const EPI ep, const MixScalars ms, const float* __restrict__ tables,
                         float* __restrict__ clean) {
   extern __shared__ __align__(16) unsigned char sm[];
   constexpr int NT = CFG::nthreads;
   const int tid = threadIdx.x;
-  // let a launch that was declared independent (RAMDSIR_FLAG_INDEPENDENT) take over SM slots as ours drain
+  const int nplanes = ms.nplanes, C = ms.C;
+  // A following launch that was found (or declared) independent may take over SM slots as ours drain; it orders
+  // itself after this grid with the griddepcontrol.wait at its own end.
   asm volatile("griddepcontrol.launch_dependents;");
   unsigned long long pol_keep, pol_stream;
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  {
-    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
-    const float4* g = reinterpret_cast<const float4*>(tables);
-    for (int i = tid; i < CFG::tabBytes / 16; i += NT) tab[i] = g[i];
+  const unsigned bar_tab = smem_u32(sm + CFG::offBar), bar_patch = bar_tab + 8;
+  if (tid == 0) {
+    mbar_init(bar_tab, 1);
+    mbar_init(bar_patch, 1);
+    mbar_init_fence();
+    mbar_expect_tx(bar_tab, CFG::tabBytes);
+    bulk_g2s(smem_u32(sm + CFG::offTab), tables, CFG::tabBytes, bar_tab);
   }
   __syncthreads();
+  mbar_wait(bar_tab, 0);
+  unsigned patch_parity = 0;
   constexpr size_t plane_px = (size_t)CFG::H * CFG::W;
-  constexpr size_t patch_px = (size_t)CFG::nb * CFG::nb;
+  constexpr int patch_px = CFG::nb * CFG::nb;
   for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
     using Quad = typename QuadOf<TIn>::type;
     const Quad* x4 = reinterpret_cast<const Quad*>(src + plane * plane_px);
     auto ld_first = [&](size_t off) { return BANK ? ldg_plain(x4 + off) : ldg_policy(x4 + off, pol_keep); };
-    Epilogue epp = ep;
+    EPI epp = ep;
     float omr = 0.f;
-    const float* patch = nullptr;
+    const float* patch = nullptr; // the partner's patch in the bank
     if (!BANK) {
       const int img = plane / C, ch = plane - img * C;
       const long long p = pidx[img];
-      const bool ok = (p >= 0 && p < (long long)n_bank);
-      if (!ok) epp.scale = __int_as_float(0x7fc00000);   // poison the plane (fminf/fmaxf swallow a NaN delta)
-      omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
+      const bool ok = (p >= 0 && p < (long long)ms.n_bank);
+      if (!ok) epp = poisoned(ep);                      // out-of-range partner: the whole plane becomes NaN
+      omr = ok ? (float)(ms.ratio_den - rk[img]) / (float)ms.ratio_den * ms.dscale : __int_as_float(0x7fc00000);
       patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
-      // pull the partner's patch (10-24 KB) towards L2 now; it is consumed after the forward columns
+      // pull the partner's patch (10-24 KB) towards L2 now; the bulk copy after the forward columns finds it there
       const char* pl = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(patch) & ~(uintptr_t)127);
-      if (tid * 128 < (int)(patch_px * 4) + 128) prefetch_l2(pl + tid * 128);
+      if (tid * 128 < patch_px * 4 + 128) prefetch_l2(pl + tid * 128);
     }
     // ---- forward columns ----
     if constexpr (CFG::smemBytes > 113 * 1024) {
@@ -213,37 +259,38 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
         }
       }
     }
-    // ---- forward rows on the band rows.  The partner patch is staged around them: its loads are issued first,
-    //      the row transforms run while they are in flight, the symmetrised values are stored afterwards ----
-    constexpr int PPT = ((int)patch_px + NT - 1) / NT;      // patch elements per thread
-    float pv[PPT], pm[PPT];
+    // ---- forward rows on the band rows.  E is idle from here to the inverse columns: the partner's patch is
+    //      bulk-copied into it (behind D) while the row transforms run ----
+    const float* P = nullptr;     // the partner's patch in shared memory (element 0)
     if (!BANK) {
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        const int i = tid + k * NT;
-        if (i < (int)patch_px) {
-          pv[k] = __ldg(patch + i);
-          pm[k] = __ldg(patch + ((int)patch_px - 1 - i));
-        }
+      // the 16-byte-aligned superset of the patch (a patch starts on any 4-byte boundary of the bank)
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(patch) & ~(uintptr_t)15;
+      const int lead = (int)(reinterpret_cast<uintptr_t>(patch) - a0);                 // 0, 4, 8 or 12
+      int bytes = (lead + patch_px * 4 + 15) & ~15;
+      // never read past the end of the bank: the last patch may be short of a full 16-byte tail
+      const uintptr_t bank_end = reinterpret_cast<uintptr_t>(bank + (size_t)ms.n_bank * C * patch_px);
+      if (a0 + bytes > bank_end) bytes = (int)((bank_end - a0) & ~(uintptr_t)15);
+      P = reinterpret_cast<const float*>(sm + CFG::offPraw + lead);
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // E was last touched through the generic proxy
+        mbar_expect_tx(bar_patch, bytes);
+        bulk_g2s(smem_u32(sm + CFG::offPraw), reinterpret_cast<const void*>(a0), bytes, bar_patch);
       }
+      const int covered = (bytes - lead) >> 2;           // patch elements the bulk copy delivers
+      if (covered < patch_px && tid < patch_px - covered)   // <= 3 tail elements, last patch of the bank only
+        reinterpret_cast<float*>(sm + CFG::offPraw + lead)[covered + tid] = __ldg(patch + covered + tid);
     }
     for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) s_row_fwd<CFG>(sm, r);
-    if (!BANK) {
-      float* P = reinterpret_cast<float*>(sm + CFG::offP);
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        const int i = tid + k * NT;
-        if (i < (int)patch_px) P[i] = 0.5f * (pv[k] + pm[k]);    // Re(ifft2) only sees the +-k average
-      }
-    }
     __syncthreads();
     if (BANK) {
-      float* patch = out + plane * patch_px;
-      for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) s_band_amp<CFG>(sm, patch, q);
+      float* po = out + (size_t)plane * patch_px;
+      for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) s_band_amp<CFG>(sm, po, q);
       __syncthreads();
       continue;
     }
-    for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) s_band_mix<CFG>(sm, omr, q);
+    mbar_wait(bar_patch, patch_parity);     // the patch has landed (requested before the row transforms)
+    patch_parity ^= 1u;
+    for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) s_band_mix<CFG>(sm, P, omr, ms.dc_add, q);
     __syncthreads();
     for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) s_row_inv<CFG>(sm, r);
     __syncthreads();
@@ -256,8 +303,8 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
       float4* c4 = DUAL ? reinterpret_cast<float4*>(clean + plane * plane_px) : nullptr;
       auto st = [&](size_t off, float4 v, float4 x) {
         stg_policy(y4 + off, v, pol_stream);
-        if (DUAL) stg_policy(c4 + off, make_float4(fmaf(x.x, ep.scale, ep.shift), fmaf(x.y, ep.scale, ep.shift),
-                                                 fmaf(x.z, ep.scale, ep.shift), fmaf(x.w, ep.scale, ep.shift)), pol_stream);
+        if (DUAL) stg_policy(c4 + off, make_float4(fmaf(x.x, ms.cscale, ms.cshift), fmaf(x.y, ms.cscale, ms.cshift),
+                                                 fmaf(x.z, ms.cscale, ms.cshift), fmaf(x.w, ms.cscale, ms.cshift)), pol_stream);
       };
       const int next = plane + gridDim.x;
       for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
@@ -288,215 +335,10 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
     }
     // next plane: its first E write happens after its loads and Z is only rewritten two barriers later
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// x2 kernel (ram_fused_x2.cuh): the static float4 pipeline with packed f32x2 arithmetic (FADD2 / FMUL2 / FFMA2).
-template <class CFG, bool BANK, bool DUAL>
-__global__ void __launch_bounds__(CFG::nthreads, (CFG::smemBytes <= 113 * 1024) ? 2 : 1)
-ram_fused_x2_kernel(const float* __restrict__ src, const float* __restrict__ bank, const int64_t* __restrict__ pidx,
-                    const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ out,
-                    const Epilogue ep, const float* __restrict__ tables, int nplanes, float* __restrict__ clean) {
-  extern __shared__ __align__(16) unsigned char sm[];
-  constexpr int NT = CFG::nthreads;
-  const int tid = threadIdx.x;
-  asm volatile("griddepcontrol.launch_dependents;");
-  unsigned long long pol_keep, pol_stream;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  {
-    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
-    const float4* g = reinterpret_cast<const float4*>(tables);
-    for (int i = tid; i < CFG::tabBytes / 16; i += NT) tab[i] = g[i];
-  }
-  __syncthreads();
-  constexpr size_t plane_px = (size_t)CFG::H * CFG::W;
-  constexpr size_t patch_px = (size_t)CFG::nb * CFG::nb;
-  const bool worker = tid < 2 * CFG::ntask;      // exchange-stage tasks: 2 parities x 128
-  const int par2 = tid >> 7, u = tid & 127;
-  for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
-    const float4* x4 = reinterpret_cast<const float4*>(src + plane * plane_px);
-    auto ld_first = [&](size_t off) { return BANK ? __ldg(x4 + off) : ldg_policy(x4 + off, pol_keep); };
-    for (int strip = 0; strip < CFG::nstrips; ++strip) {
-      cf2 v[16];
-      x_f1_load_fft_tw<CFG>(ld_first, sm, strip, tid, v);
-      if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        x_f1_store_half<CFG>(sm, tid, half, v);
-        __syncthreads();
-        if (worker) {
-          if (par2 == 0) x_f1_pruned<CFG, 0>(sm, strip, half, u);
-          else x_f1_pruned<CFG, 1>(sm, strip, half, u);
-        }
-        __syncthreads();
-      }
-    }
-    Epilogue epp = ep;
-    float omr = 0.f;
-    if (!BANK) {
-      const int img = plane / C, ch = plane - img * C;
-      const long long p = pidx[img];
-      const bool ok = (p >= 0 && p < (long long)n_bank);
-      if (!ok) epp.scale = __int_as_float(0x7fc00000);
-      omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
-      const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
-      for (int i = tid; i < (int)patch_px; i += NT) s_stage_patch<CFG>(sm, patch, i);
-    }
-    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) x_row_fwd<CFG>(sm, r);
-    __syncthreads();
-    if (BANK) {
-      float* po = out + plane * patch_px;
-      for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) x_band_amp<CFG>(sm, po, q);
-      __syncthreads();
-      continue;
-    }
-    for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) x_band_mix<CFG>(sm, omr, q);
-    __syncthreads();
-    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) x_row_inv<CFG>(sm, r);
-    __syncthreads();
-    {
-      float4* y4 = reinterpret_cast<float4*>(out + plane * plane_px);
-      auto ld_again = [&](size_t off) { return ldg_policy(x4 + off, pol_stream); };
-      float4* c4 = DUAL ? reinterpret_cast<float4*>(clean + plane * plane_px) : nullptr;
-      auto st = [&](size_t off, float4 v, float4 x) {
-        stg_policy(y4 + off, v, pol_stream);
-        if (DUAL) stg_policy(c4 + off, make_float4(fmaf(x.x, ep.scale, ep.shift), fmaf(x.y, ep.scale, ep.shift),
-                                                   fmaf(x.z, ep.scale, ep.shift), fmaf(x.w, ep.scale, ep.shift)), pol_stream);
-      };
-      const int next = plane + gridDim.x;
-      for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
-        cf2 ev[8], od[8];
-        if (strip > 0) prefetch_strip<CFG>(x4, strip - 1, tid);
-        else if (next < nplanes) prefetch_strip<CFG>(reinterpret_cast<const float4*>(src + next * plane_px), 0, tid);
-        if (worker) {
-          if (par2 == 0) x_inv_pruned<CFG, 0>(sm, strip, 0, u);
-          else x_inv_pruned<CFG, 1>(sm, strip, 0, u);
-        }
-        __syncthreads();
-        x_inv_fft8<CFG>(sm, tid, 0, ev);
-        __syncthreads();
-        if (worker) {
-          if (par2 == 0) x_inv_pruned<CFG, 0>(sm, strip, 1, u);
-          else x_inv_pruned<CFG, 1>(sm, strip, 1, u);
-        }
-        __syncthreads();
-        x_inv_fft8<CFG>(sm, tid, 1, od);
-        __syncthreads();
-        x_inv_combine_store<CFG>(ld_again, st, epp, strip, tid, ev, od);
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// P2 kernel (ram_fused_p2.cuh): one packed complex column per thread, 64 registers, 1024 threads/SM.
-__device__ __forceinline__ float2 ldg_policy2(const float2* p, unsigned long long pol) {
-  float2 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ void stg_policy2(float2* p, float2 v, unsigned long long pol) {
-  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
-}
-// a warp (one h1, 32 columns) loads 16 rows x 256 bytes per strip = 32 lines: one prefetch per lane
-template <class CFG>
-__device__ __forceinline__ void prefetch_strip_p2(const float2* x2, int strip, int tid) {
-  const int lane = tid & 31, h1 = tid >> 5;
-  prefetch_l2(x2 + (size_t)(h1 + CFG::N1h * (lane >> 1)) * CFG::M2 + strip * 32 + (lane & 1) * 16);
-}
-
-template <class CFG, bool BANK>
-__global__ void __launch_bounds__(CFG::nthreads, (CFG::smemBytes <= 113 * 1024) ? 2 : 1)
-ram_fused_p2_kernel(const float* __restrict__ src, const float* __restrict__ bank, const int64_t* __restrict__ pidx,
-                    const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ out,
-                    const Epilogue ep, const float* __restrict__ tables, int nplanes) {
-  extern __shared__ __align__(16) unsigned char sm[];
-  constexpr int NT = CFG::nthreads;
-  const int tid = threadIdx.x;
-  // let a launch that was declared independent (RAMDSIR_FLAG_INDEPENDENT) take over SM slots as ours drain
-  asm volatile("griddepcontrol.launch_dependents;");
-  unsigned long long pol_keep, pol_stream;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  {
-    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
-    const float4* g = reinterpret_cast<const float4*>(tables);
-    for (int i = tid; i < CFG::tabBytes / 16; i += NT) tab[i] = g[i];
-  }
-  __syncthreads();
-  constexpr size_t plane_px = (size_t)CFG::H * CFG::W;
-  constexpr size_t patch_px = (size_t)CFG::nb * CFG::nb;
-  const bool worker = tid < CFG::npruned;          // pruned-stage tasks: 2 parities x 256
-  const int par2 = tid >> 8, u = tid & 255;
-  for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
-    const float2* x2 = reinterpret_cast<const float2*>(src + plane * plane_px);
-    auto ld_first = [&](size_t off) { return BANK ? __ldg(x2 + off) : ldg_policy2(x2 + off, pol_keep); };
-    for (int strip = 0; strip < CFG::nstrips; ++strip) {
-      cf v[16];
-      p_f1_load_fft_tw<CFG>(ld_first, sm, strip, tid, v);
-      if (strip + 1 < CFG::nstrips) prefetch_strip_p2<CFG>(x2, strip + 1, tid);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        p_f1_store_half<CFG>(sm, tid, half, v);
-        __syncthreads();
-        if (worker) {
-          if (par2 == 0) p_f1_pruned<CFG, 0>(sm, strip, half, u);
-          else p_f1_pruned<CFG, 1>(sm, strip, half, u);
-        }
-        __syncthreads();
-      }
-    }
-    Epilogue epp = ep;
-    float omr = 0.f;
-    if (!BANK) {
-      const int img = plane / C, ch = plane - img * C;
-      const long long p = pidx[img];
-      const bool ok = (p >= 0 && p < (long long)n_bank);
-      if (!ok) epp.scale = __int_as_float(0x7fc00000);
-      omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
-      const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * patch_px;
-      for (int i = tid; i < (int)patch_px; i += NT) s_stage_patch<CFG>(sm, patch, i);
-    }
-    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) p_row_fwd<CFG>(sm, r);
-    __syncthreads();
-    if (BANK) {
-      float* patch = out + plane * patch_px;
-      for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) p_band_amp<CFG>(sm, patch, q);
-      __syncthreads();
-      continue;
-    }
-    for (int q = tid; q < CFG::nb * (CFG::b + 1); q += NT) p_band_mix<CFG>(sm, omr, q);
-    __syncthreads();
-    for (int r = tid; r < CFG::nb * CFG::N1w; r += NT) p_row_inv<CFG>(sm, r);
-    __syncthreads();
-    {
-      float2* y2 = reinterpret_cast<float2*>(out + plane * plane_px);
-      auto ld_again = [&](size_t off) { return ldg_policy2(x2 + off, pol_stream); };
-      auto st = [&](size_t off, float2 v) { stg_policy2(y2 + off, v, pol_stream); };
-      const int next = plane + gridDim.x;
-      for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
-        cf ev[8], od[8];
-        if (strip > 0) prefetch_strip_p2<CFG>(x2, strip - 1, tid);
-        else if (next < nplanes) prefetch_strip_p2<CFG>(reinterpret_cast<const float2*>(src + next * plane_px), 0, tid);
-        if (worker) {
-          if (par2 == 0) p_inv_pruned<CFG, 0>(sm, strip, 0, u);
-          else p_inv_pruned<CFG, 1>(sm, strip, 0, u);
-        }
-        __syncthreads();
-        p_inv_fft8<CFG>(sm, tid, 0, ev);
-        __syncthreads();
-        if (worker) {
-          if (par2 == 0) p_inv_pruned<CFG, 0>(sm, strip, 1, u);
-          else p_inv_pruned<CFG, 1>(sm, strip, 1, u);
-        }
-        __syncthreads();
-        p_inv_fft8<CFG>(sm, tid, 1, od);
-        __syncthreads();
-        p_inv_combine_store<CFG>(ld_again, st, epp, strip, tid, ev, od);
-      }
-    }
-  }
+  // Programmatic dependent launch: this grid may have started before the previous kernel in the stream finished.
+  // Do not let it COMPLETE before that kernel has (completion and memory flush), so that whatever the stream runs
+  // next (a copy of the previous batch, a consumer kernel) is ordered after both.  No-op for a plain launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -505,38 +347,27 @@ struct FusedPlan {
   FusedShape S;
   float* tables = nullptr;  // device
   int sm_count = 0;
-  int static_id = 0;        // 0: runtime-shape kernel; 1/2: SCfg<256..>/<384..> (float4); 3/4: PCfg (float2, default)
+  int static_id = 0;        // 0: runtime-shape kernel; 1: SCfg<256,256,25>; 2: SCfg<384,384,38>
 };
 using Cfg256 = SCfg<256, 256, 25>;
 using Cfg384 = SCfg<384, 384, 38>;
-using P256 = PCfg<256, 256, 25>;
-using P384 = PCfg<384, 384, 38>;
-using X256 = XCfg<256, 256, 25>;
-using X384 = XCfg<384, 384, 38>;
-thread_local float* t_clean = nullptr;   // fused dual output target of the calling thread's current call (or null)
-thread_local int t_overlap = 0;   // per-call flag of the calling thread (set by fused_mix, read by launch_static)
-std::atomic<int> g_variant{0};   // RAMDSIR_VARIANT_*: 0 auto (= float4 static kernels), 1 P2, 2 runtime-shape
-int static_id_of(int H, int W, int b, int variant) {
-  if (variant == 2) return 0;
-  if (variant == 4) {
-    if (H == 256 && W == 256 && b == 25) return 7;
-    if (H == 384 && W == 384 && b == 38) return 8;
-    return 0;
-  }
-  const int base = (variant == 1) ? 2 : 0;
-  if (H == 256 && W == 256 && b == 25) return base + 1;
-  if (H == 384 && W == 384 && b == 38) return base + 2;
+
+int static_id_of(int H, int W, int b) {
+  if (H == 256 && W == 256 && b == 25) return 1;
+  if (H == 384 && W == 384 && b == 38) return 2;
   return 0;
 }
 std::mutex g_mu;
-std::map<std::tuple<int, int, int, int, int>, FusedPlan> g_plans;  // (device, H, W, b, variant)
+std::map<std::tuple<int, int, int, int, int>, FusedPlan> g_plans;  // (device, H, W, b, runtime-shape?)
+std::map<int, cudaStream_t> g_upload_stream;                       // per device, for table uploads
 
-int get_plan(int H, int W, int b, FusedPlan** out) {
+// Tables are uploaded on a private stream and that stream alone is synchronised: first use of a shape blocks the
+// calling host thread for the few microseconds of a 7 KB copy, but never the device or anybody else's stream.
+int get_plan(int H, int W, int b, bool runtime_shape, FusedPlan** out) {
   int dev = 0;
   RD_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_mu);
-  const int variant = g_variant.load(std::memory_order_relaxed);
-  auto key = std::make_tuple(dev, H, W, b, variant);
+  auto key = std::make_tuple(dev, H, W, b, runtime_shape ? 1 : 0);
   auto it = g_plans.find(key);
   if (it == g_plans.end()) {
     FusedPlan p;
@@ -544,21 +375,17 @@ int get_plan(int H, int W, int b, FusedPlan** out) {
       set_error("fused path does not support H=%d W=%d b=%d", H, W, b);
       return RAMDSIR_ERR_UNSUPPORTED;
     }
-    p.static_id = static_id_of(H, W, b, variant);
-    const int tab_bytes = p.static_id == 1 ? Cfg256::tabBytes : p.static_id == 2 ? Cfg384::tabBytes
-                        : p.static_id == 3 ? P256::tabBytes : p.static_id == 4 ? P384::tabBytes
-                        : p.static_id == 7 ? X256::tabBytes : p.static_id == 8 ? X384::tabBytes : p.S.tabBytes;
+    p.static_id = runtime_shape ? 0 : static_id_of(H, W, b);
+    const int tab_bytes = p.static_id == 1 ? Cfg256::tabBytes : p.static_id == 2 ? Cfg384::tabBytes : p.S.tabBytes;
     std::vector<float> host(tab_bytes / 4);
     if (p.static_id == 1) fused_tables_fill_static<Cfg256>(host.data());
     else if (p.static_id == 2) fused_tables_fill_static<Cfg384>(host.data());
-    else if (p.static_id == 3) fused_tables_fill_p2<P256>(host.data());
-    else if (p.static_id == 4) fused_tables_fill_p2<P384>(host.data());
-    else if (p.static_id == 7) fused_tables_fill_x2<X256>(host.data());
-    else if (p.static_id == 8) fused_tables_fill_x2<X384>(host.data());
     else fused_tables_fill(p.S, host.data());
+    cudaStream_t& up = g_upload_stream[dev];
+    if (!up) RD_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
     RD_CUDA(cudaMalloc(&p.tables, tab_bytes));
-    RD_CUDA(cudaMemcpy(p.tables, host.data(), tab_bytes, cudaMemcpyHostToDevice));
-    RD_CUDA(cudaDeviceSynchronize());  // once per shape: tables are visible to every stream afterwards
+    RD_CUDA(cudaMemcpyAsync(p.tables, host.data(), tab_bytes, cudaMemcpyHostToDevice, up));
+    RD_CUDA(cudaStreamSynchronize(up));   // `host` dies at scope exit; the tables are complete for every stream
     RD_CUDA(cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev));
     it = g_plans.emplace(key, p).first;
   }
@@ -566,6 +393,55 @@ int get_plan(int H, int W, int b, FusedPlan** out) {
   return RAMDSIR_OK;
 }
 
+// ---- automatic overlap of consecutive launches -------------------------------------------------------------
+// A static fused launch may start while the previous fused launch in the same stream drains its last wave
+// (programmatic dependent launch) when the two touch disjoint memory: nothing this launch reads or writes was written
+// by that launch, and nothing it writes was read by it.  The library knows every buffer of both launches, so it
+// decides this itself; the caller's RAMDSIR_FLAG_INDEPENDENT only skips the check.  The last TWO launches are
+// compared because launch N+2 can start as soon as N+1 has started all its CTAs, i.e. when N's CTAs have exited but
+// before N is formally complete.  Anything else the library enqueues on the stream clears the trail.
+struct Range { uintptr_t lo, hi; };
+struct LaunchFootprint { Range rd[4]; int nrd = 0; Range wr[2]; int nwr = 0; };
+struct Trail { LaunchFootprint last[2]; int n = 0; };
+std::mutex g_trail_mu;
+std::map<std::pair<int, cudaStream_t>, Trail> g_trails;
+
+bool overlaps(const Range& a, const Range& b) { return a.lo < b.hi && b.lo < a.hi; }
+bool conflicts(const LaunchFootprint& cur, const LaunchFootprint& prev) {
+  for (int i = 0; i < prev.nwr; ++i) {
+    for (int j = 0; j < cur.nrd; ++j) if (overlaps(prev.wr[i], cur.rd[j])) return true;   // read after write
+    for (int j = 0; j < cur.nwr; ++j) if (overlaps(prev.wr[i], cur.wr[j])) return true;   // write after write
+  }
+  for (int i = 0; i < prev.nrd; ++i)
+    for (int j = 0; j < cur.nwr; ++j) if (overlaps(prev.rd[i], cur.wr[j])) return true;   // write after read
+  return false;
+}
+const bool g_auto_overlap = [] { const char* e = getenv("RAMDSIR_NO_AUTO_OVERLAP"); return !(e && e[0] == '1'); }();
+
+// Returns whether `cur` may be launched with programmatic stream serialisation, and records it as the newest launch.
+bool trail_push(int dev, cudaStream_t st, const LaunchFootprint& cur, bool assume_independent) {
+  std::lock_guard<std::mutex> lk(g_trail_mu);
+  Trail& t = g_trails[{dev, st}];
+  bool ok = t.n > 0;                               // nothing of ours precedes: a plain launch
+  if (ok && !assume_independent) {
+    ok = g_auto_overlap;
+    for (int i = 0; ok && i < t.n; ++i) ok = !conflicts(cur, t.last[i]);
+  }
+  t.last[1] = t.last[0];
+  t.last[0] = cur;
+  if (t.n < 2) ++t.n;
+  return ok;
+}
+}  // namespace
+
+void fused_trail_reset(cudaStream_t st) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  std::lock_guard<std::mutex> lk(g_trail_mu);
+  g_trails.erase({dev, st});
+}
+
+namespace {
 template <int MMAX, bool BANK>
 int launch(const FusedPlan& p, const float* src, const float* bank, const int64_t* pidx, const int32_t* rk,
            int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
@@ -583,89 +459,109 @@ int launch(const FusedPlan& p, const float* src, const float* bank, const int64_
   if (per_sm < 1) per_sm = 1;
   int grid = p.sm_count * per_sm;
   if (grid > nplanes) grid = nplanes;
+  fused_trail_reset(st);
   kern<<<grid, p.S.nthreads, p.S.smemBytes, st>>>(p.S, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes);
   count_launch();
   RD_CUDA(cudaGetLastError());
   return RAMDSIR_OK;
 }
 
-template <class CFG, bool BANK, class TIn = float>
-struct KernelOf {
-  static constexpr bool dual = true;    // takes the extra `clean` pointer; a second instantiation writes it
-  static auto get() { return ram_fused_static_kernel<CFG, BANK, false, TIn>; }
-  static auto get_dual() { return ram_fused_static_kernel<CFG, BANK, !BANK, TIn>; }
-};
-template <int H, int W, int B, bool BANK>
-struct KernelOf<PCfg<H, W, B>, BANK, float> {
-  static constexpr bool dual = false;
-  static auto get() { return ram_fused_p2_kernel<PCfg<H, W, B>, BANK>; }
+// EpiSat parameters of a finite clip range (see ram_fused_static.cuh): computed in double, rounded once.
+bool epilogue_sat(const Epilogue& e, EpiSat& s, float& dscale, float& dc_add) {
+  if (!(std::isfinite(e.lo) && std::isfinite(e.hi) && e.hi > e.lo)) return false;
+  const double span = (double)e.hi - (double)e.lo;
+  s.a = (float)(1.0 / span);
+  s.m = (float)(span * (double)e.scale);
+  s.t = (float)((double)e.lo * (double)e.scale + (double)e.shift);
+  dscale = s.a;
+  dc_add = (float)(-(double)e.lo / span);
+  return std::isfinite(s.a) && std::isfinite(s.m) && std::isfinite(s.t);
+}
+
+struct StaticArgs {
+  const void* src; size_t src_bytes;      // float or uint8 planes
+  const float* bank; const int64_t* pidx; const int32_t* rk;
+  float* out; float* clean;
+  int ratio_den, n_bank, C, nplanes, nimg;
+  Epilogue ep;
+  unsigned flags;
 };
 
-template <int H, int W, int B, bool BANK>
-struct KernelOf<XCfg<H, W, B>, BANK, float> {
-  static constexpr bool dual = true;
-  static auto get() { return ram_fused_x2_kernel<XCfg<H, W, B>, BANK, false>; }
-  static auto get_dual() { return ram_fused_x2_kernel<XCfg<H, W, B>, BANK, !BANK>; }
-};
-
-template <class CFG, bool BANK, class TIn = float>
-int launch_static(const FusedPlan& p, const TIn* src, const float* bank, const int64_t* pidx, const int32_t* rk,
-                  int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
-  using KO = KernelOf<CFG, BANK, TIn>;
-  auto kern = KO::get();
-  if constexpr (KO::dual) {
-    if (t_clean && !BANK) kern = KO::get_dual();
-  }
+template <class CFG, bool BANK, bool DUAL, class TIn, class EPI>
+int launch_static_one(const FusedPlan& p, const StaticArgs& a, const EPI& epi, const MixScalars& ms, bool pdl, cudaStream_t st) {
+  auto kern = ram_fused_static_kernel<CFG, BANK, DUAL, TIn, EPI>;
   // cudaFuncSetAttribute and occupancy are per device: cache per (instantiation, device)
   static thread_local int per_sm_dev[64] = {0};
   int dev = 0;
   RD_CUDA(cudaGetDevice(&dev));
   int& per_sm = per_sm_dev[dev & 63];
   if (per_sm == 0) {
-    RD_CUDA(cudaFuncSetAttribute(KO::get(), cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
-    if constexpr (KO::dual)   // whichever of the two instantiations this first call uses, configure both
-      RD_CUDA(cudaFuncSetAttribute(KO::get_dual(), cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
+    RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
     RD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::nthreads, CFG::smemBytes));
     if (per_sm < 1) per_sm = 1;
   }
   int grid = p.sm_count * per_sm;
-  if (grid > nplanes) grid = nplanes;
-  if (t_overlap && !BANK) {
-    // programmatic dependent launch: do not wait for the previous kernel in the stream to finish
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(CFG::nthreads);
-    cfg.dynamicSmemBytes = CFG::smemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if constexpr (KO::dual)
-      RD_CUDA(cudaLaunchKernelEx(&cfg, kern, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, (const float*)p.tables, nplanes, t_clean));
-    else
-      RD_CUDA(cudaLaunchKernelEx(&cfg, kern, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, (const float*)p.tables, nplanes));
-  } else {
-    if constexpr (KO::dual)
-      kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes, BANK ? nullptr : t_clean);
-    else
-      kern<<<grid, CFG::nthreads, CFG::smemBytes, st>>>(src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, p.tables, nplanes);
-  }
+  if (grid > a.nplanes) grid = a.nplanes;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CFG::nthreads);
+  cfg.dynamicSmemBytes = CFG::smemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  RD_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<const TIn*>(a.src), a.bank, a.pidx, a.rk, a.out, epi, ms,
+                             (const float*)p.tables, a.clean));
   count_launch();
   RD_CUDA(cudaGetLastError());
   return RAMDSIR_OK;
 }
 
+template <class CFG, bool BANK, class TIn>
+int launch_static(const FusedPlan& p, const StaticArgs& a, cudaStream_t st) {
+  int dev = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  constexpr size_t patch_bytes = (size_t)CFG::nb * CFG::nb * 4;
+  auto rng = [](const void* q, size_t n) { return Range{reinterpret_cast<uintptr_t>(q), reinterpret_cast<uintptr_t>(q) + n}; };
+  LaunchFootprint fp;
+  fp.rd[fp.nrd++] = rng(a.src, a.src_bytes);
+  MixScalars ms{a.ratio_den, a.n_bank, a.C, a.nplanes, 1.f, 0.f, a.ep.scale, a.ep.shift};
+  if (BANK) {
+    fp.wr[fp.nwr++] = rng(a.out, (size_t)a.nplanes * patch_bytes);
+    trail_push(dev, st, fp, false);       // recorded (a following mix reads this bank); itself a plain launch
+    return launch_static_one<CFG, true, false, TIn, EpiClamp>(p, a, EpiClamp{0, 0, 1, 0}, ms, false, st);
+  } else {
+    fp.rd[fp.nrd++] = rng(a.bank, (size_t)a.n_bank * a.C * patch_bytes);
+    fp.rd[fp.nrd++] = rng(a.pidx, (size_t)a.nimg * sizeof(int64_t));
+    fp.rd[fp.nrd++] = rng(a.rk, (size_t)a.nimg * sizeof(int32_t));
+    const size_t out_bytes = (size_t)a.nplanes * CFG::H * CFG::W * 4;
+    fp.wr[fp.nwr++] = rng(a.out, out_bytes);
+    if (a.clean) fp.wr[fp.nwr++] = rng(a.clean, out_bytes);
+    const bool pdl = trail_push(dev, st, fp, (a.flags & RAMDSIR_FLAG_INDEPENDENT) != 0) && !(a.flags & RAMDSIR_FLAG_SERIAL);
+    EpiSat es;
+    if (epilogue_sat(a.ep, es, ms.dscale, ms.dc_add)) {
+      if (a.clean) return launch_static_one<CFG, false, true, TIn, EpiSat>(p, a, es, ms, pdl, st);
+      return launch_static_one<CFG, false, false, TIn, EpiSat>(p, a, es, ms, pdl, st);
+    }
+    ms.dscale = 1.f;
+    ms.dc_add = 0.f;
+    const EpiClamp ec{a.ep.lo, a.ep.hi, a.ep.scale, a.ep.shift};
+    if (a.clean) return launch_static_one<CFG, false, true, TIn, EpiClamp>(p, a, ec, ms, pdl, st);
+    return launch_static_one<CFG, false, false, TIn, EpiClamp>(p, a, ec, ms, pdl, st);
+  }
+}
+
+template <bool BANK, class TIn>
+int dispatch_static(const FusedPlan& p, const StaticArgs& a, cudaStream_t st) {
+  if (p.static_id == 1) return launch_static<Cfg256, BANK, TIn>(p, a, st);
+  return launch_static<Cfg384, BANK, TIn>(p, a, st);
+}
+
 template <bool BANK>
-int dispatch(const FusedPlan& p, const float* src, const float* bank, const int64_t* pidx, const int32_t* rk,
-             int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
-  if (p.static_id == 1) return launch_static<Cfg256, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
-  if (p.static_id == 2) return launch_static<Cfg384, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
-  if (p.static_id == 3) return launch_static<P256, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
-  if (p.static_id == 4) return launch_static<P384, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
-  if (p.static_id == 7) return launch_static<X256, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
-  if (p.static_id == 8) return launch_static<X384, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
+int dispatch_runtime(const FusedPlan& p, const float* src, const float* bank, const int64_t* pidx, const int32_t* rk,
+                     int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
   switch (p.S.MM) {
     case 0:
     case 1: return launch<1, BANK>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
@@ -676,64 +572,72 @@ int dispatch(const FusedPlan& p, const float* src, const float* bank, const int6
   set_error("band half-width %d too large for the fused path", p.S.b);
   return RAMDSIR_ERR_UNSUPPORTED;
 }
-
-template <bool BANK>
-int dispatch_u8(const FusedPlan& p, const unsigned char* src, const float* bank, const int64_t* pidx, const int32_t* rk,
-                int ratio_den, int n_bank, int C, float* out, Epilogue ep, int nplanes, cudaStream_t st) {
-  if (p.static_id == 1) return launch_static<Cfg256, BANK, unsigned char>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
-  if (p.static_id == 2) return launch_static<Cfg384, BANK, unsigned char>(p, src, bank, pidx, rk, ratio_den, n_bank, C, out, ep, nplanes, st);
-  set_error("uint8 sources are read directly only by the static fused kernels (256x256/b=25, 384x384/b=38)");
-  return RAMDSIR_ERR_UNSUPPORTED;
-}
 }  // namespace
 
-bool fused_u8_supported(int H, int W, int b) {
-  const int id = static_id_of(H, W, b, g_variant.load(std::memory_order_relaxed));
-  return id == 1 || id == 2;
+bool fused_static_shape(int H, int W, int b) { return static_id_of(H, W, b) != 0; }
+bool fused_u8_supported(int H, int W, int b) { return fused_static_shape(H, W, b); }
+bool fused_dual_supported(int H, int W, int b, unsigned flags) {
+  return fused_static_shape(H, W, b) && !(flags & RAMDSIR_FLAG_RUNTIME_SHAPE);
 }
-
-int fused_mix_u8(const MixArgs& a, const unsigned char* src, cudaStream_t st) {
-  FusedPlan* p = nullptr;
-  int rc = get_plan(a.H, a.W, a.b, &p);
-  if (rc) return rc;
-  t_overlap = a.independent ? 1 : 0;
-  t_clean = a.clean;
-  return dispatch_u8<false>(*p, src, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, a.out, a.ep, a.B * a.C, st);
-}
-
-int fused_bank_u8(const unsigned char* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st) {
-  FusedPlan* p = nullptr;
-  int rc = get_plan(H, W, b, &p);
-  if (rc) return rc;
-  return dispatch_u8<true>(*p, imgs, nullptr, nullptr, nullptr, 10, 0, C, bank, Epilogue{0, 0, 1, 0}, N * C, st);
-}
-
-bool fused_dual_supported(int H, int W, int b) {
-  const int id = static_id_of(H, W, b, g_variant.load(std::memory_order_relaxed));
-  return id == 1 || id == 2 || id == 7 || id == 8;
-}
-
-void fused_set_variant(int v) { g_variant.store(v, std::memory_order_relaxed); }
 
 bool fused_supported(int H, int W, int b) {
   FusedShape S;
   return fused_shape_init(S, H, W, b);
 }
 
-int fused_mix(const MixArgs& a, cudaStream_t st) {
+int fused_prepare(int H, int W, int b) {
   FusedPlan* p = nullptr;
-  int rc = get_plan(a.H, a.W, a.b, &p);
-  if (rc) return rc;
-  t_overlap = a.independent ? 1 : 0;
-  t_clean = (p->static_id == 1 || p->static_id == 2 || p->static_id == 7 || p->static_id == 8) ? a.clean : nullptr;
-  return dispatch<false>(*p, a.src, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, a.out, a.ep, a.B * a.C, st);
+  return get_plan(H, W, b, false, &p);
 }
 
-int fused_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st) {
+int fused_mix_u8(const MixArgs& a, const unsigned char* src, cudaStream_t st) {
   FusedPlan* p = nullptr;
-  int rc = get_plan(H, W, b, &p);
+  int rc = get_plan(a.H, a.W, a.b, false, &p);
   if (rc) return rc;
-  return dispatch<true>(*p, imgs, nullptr, nullptr, nullptr, 10, 0, C, bank, Epilogue{0, 0, 1, 0}, N * C, st);
+  if (!p->static_id) {
+    set_error("uint8 sources are read directly only by the static fused kernels (256x256/b=25, 384x384/b=38)");
+    return RAMDSIR_ERR_UNSUPPORTED;
+  }
+  const StaticArgs s{src, (size_t)a.B * a.C * a.H * a.W, a.bank, a.pidx, a.rk, a.out, a.clean,
+                     a.ratio_den, a.n_bank, a.C, a.B * a.C, a.B, a.ep, a.flags};
+  return dispatch_static<false, unsigned char>(*p, s, st);
+}
+
+int fused_bank_u8(const unsigned char* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st) {
+  FusedPlan* p = nullptr;
+  int rc = get_plan(H, W, b, false, &p);
+  if (rc) return rc;
+  if (!p->static_id) {
+    set_error("uint8 sources are read directly only by the static fused kernels (256x256/b=25, 384x384/b=38)");
+    return RAMDSIR_ERR_UNSUPPORTED;
+  }
+  const StaticArgs s{imgs, (size_t)N * C * H * W, nullptr, nullptr, nullptr, bank, nullptr, 10, 0, C, N * C, N,
+                     Epilogue{0, 0, 1, 0}, 0u};
+  return dispatch_static<true, unsigned char>(*p, s, st);
+}
+
+int fused_mix(const MixArgs& a, cudaStream_t st) {
+  FusedPlan* p = nullptr;
+  int rc = get_plan(a.H, a.W, a.b, (a.flags & RAMDSIR_FLAG_RUNTIME_SHAPE) != 0, &p);
+  if (rc) return rc;
+  if (p->static_id) {
+    const StaticArgs s{a.src, (size_t)a.B * a.C * a.H * a.W * 4, a.bank, a.pidx, a.rk, a.out, a.clean,
+                       a.ratio_den, a.n_bank, a.C, a.B * a.C, a.B, a.ep, a.flags};
+    return dispatch_static<false, float>(*p, s, st);
+  }
+  return dispatch_runtime<false>(*p, a.src, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, a.out, a.ep, a.B * a.C, st);
+}
+
+int fused_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, unsigned flags, cudaStream_t st) {
+  FusedPlan* p = nullptr;
+  int rc = get_plan(H, W, b, (flags & RAMDSIR_FLAG_RUNTIME_SHAPE) != 0, &p);
+  if (rc) return rc;
+  if (p->static_id) {
+    const StaticArgs s{imgs, (size_t)N * C * H * W * 4, nullptr, nullptr, nullptr, bank, nullptr, 10, 0, C, N * C, N,
+                       Epilogue{0, 0, 1, 0}, 0u};
+    return dispatch_static<true, float>(*p, s, st);
+  }
+  return dispatch_runtime<true>(*p, imgs, nullptr, nullptr, nullptr, 10, 0, C, bank, Epilogue{0, 0, 1, 0}, N * C, st);
 }
 
 }  // namespace ramdsir

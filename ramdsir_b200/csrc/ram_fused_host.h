@@ -5,8 +5,6 @@
 #include <vector>
 #include "ram_fused_core.cuh"
 #include "ram_fused_static.cuh"
-#include "ram_fused_p2.cuh"
-#include "ram_fused_x2.cuh"
 
 namespace ramdsir {
 
@@ -107,68 +105,6 @@ inline void fused_tables_fill_static(float* tab) {
       const long n = ((long)c1 * k2) % CFG::M;
       tab[CFG::tTWM + 2 * (c1 * 16 + k2)] = (float)ct::cos2pi(n, CFG::M);
       tab[CFG::tTWM + 2 * (c1 * 16 + k2) + 1] = (float)-ct::sin2pi(n, CFG::M);
-    }
-}
-
-// x2 kernels (packed arithmetic): PT in RRII order, TW3, TWH2 / TWM2 with the twiddle broadcast to both lanes
-template <class CFG>
-inline void fused_tables_fill_x2(float* tab) {
-  for (int i = 0; i < CFG::tabBytes / 4; ++i) tab[i] = 0.f;
-  auto eW = [&](long n, double& re, double& im) { re = ct::cos2pi(n, CFG::W); im = ct::sin2pi(n, CFG::W); };  // exp(+2 pi i n / W)
-  for (int c1 = 0; c1 < CFG::N1w; ++c1)
-    for (int kwi = 0; kwi < CFG::nb; ++kwi) {
-      const long kw = kwi - CFG::b;
-      double r1, i1, r2, i2, r3, i3, rm, im;
-      eW(kw, r1, i1); eW(2 * kw, r2, i2); eW(3 * kw, r3, i3); eW(4L * c1 * kw, rm, im);
-      const double qar = 1.0 - i2, qai = r2, qbr = r1 - i3, qbi = i1 + r3;
-      float* p = tab + CFG::tPT + 4 * (c1 * CFG::nb + kwi);
-      p[0] = (float)(qar * rm - qai * im); p[1] = (float)(qbr * rm - qbi * im);   // re: a, b
-      p[2] = (float)(qar * im + qai * rm); p[3] = (float)(qbr * im + qbi * rm);   // im: a, b
-    }
-  for (int g = 1; g <= 3; ++g)
-    for (int kw = 0; kw <= CFG::b; ++kw) {
-      tab[CFG::tTW3 + 2 * ((g - 1) * (CFG::b + 1) + kw)] = (float)ct::cos2pi((long)g * kw, CFG::W);
-      tab[CFG::tTW3 + 2 * ((g - 1) * (CFG::b + 1) + kw) + 1] = (float)-ct::sin2pi((long)g * kw, CFG::W);
-    }
-  for (int h1 = 0; h1 < CFG::N1h; ++h1)
-    for (int k2 = 0; k2 < 16; ++k2) {
-      const long n = ((long)h1 * k2) % CFG::H;
-      float* p = tab + CFG::tTWH2 + 4 * (h1 * CFG::tw4Pitch + k2);
-      p[0] = p[1] = (float)ct::cos2pi(n, CFG::H);
-      p[2] = p[3] = (float)-ct::sin2pi(n, CFG::H);
-    }
-  for (int c1 = 0; c1 < CFG::N1w; ++c1)
-    for (int k2 = 0; k2 < 16; ++k2) {
-      const long n = ((long)c1 * k2) % CFG::M;
-      float* p = tab + CFG::tTWM2 + 4 * (c1 * 16 + k2);
-      p[0] = p[1] = (float)ct::cos2pi(n, CFG::M);
-      p[2] = p[3] = (float)-ct::sin2pi(n, CFG::M);
-    }
-}
-
-// P2 kernels (one packed complex column per thread): PT, TW3, TWH, TWM
-template <class CFG>
-inline void fused_tables_fill_p2(float* tab) {
-  for (int i = 0; i < CFG::tabBytes / 4; ++i) tab[i] = 0.f;
-  auto put = [&](int idx, double re, double im) { tab[idx] = (float)re; tab[idx + 1] = (float)im; };
-  for (int c1 = 0; c1 < CFG::N1w; ++c1)
-    for (int kwi = 0; kwi < CFG::nb; ++kwi) {
-      const long kw = kwi - CFG::b;
-      const double r1 = ct::cos2pi(kw, CFG::W), i1 = ct::sin2pi(kw, CFG::W);          // W_W^-kw
-      const double rm = ct::cos2pi(2L * c1 * kw, CFG::W), im = ct::sin2pi(2L * c1 * kw, CFG::W);  // W_M2^(-c1 kw)
-      const double qr = 1.0 - i1, qi = r1;                                             // 1 + i W_W^-kw
-      put(CFG::tPT + 2 * (c1 * CFG::nb + kwi), qr * rm - qi * im, qr * im + qi * rm);
-    }
-  for (int kw = 0; kw <= CFG::b; ++kw) put(CFG::tTW3 + 2 * kw, ct::cos2pi(kw, CFG::W), -ct::sin2pi(kw, CFG::W));
-  for (int h1 = 0; h1 < CFG::N1h; ++h1)
-    for (int k2 = 0; k2 < 16; ++k2) {
-      const long n = ((long)h1 * k2) % CFG::H;
-      put(CFG::tTWH + 2 * (h1 * CFG::twhPitch + k2), ct::cos2pi(n, CFG::H), -ct::sin2pi(n, CFG::H));
-    }
-  for (int c1 = 0; c1 < CFG::N1w; ++c1)
-    for (int k2 = 0; k2 < 16; ++k2) {
-      const long n = ((long)c1 * k2) % CFG::M2;
-      put(CFG::tTWM + 2 * (c1 * 16 + k2), ct::cos2pi(n, CFG::M2), -ct::sin2pi(n, CFG::M2));
     }
 }
 

@@ -36,10 +36,9 @@ struct SCfg {
   static constexpr int zBytes = s_al16(nb * pitchZ * 16);
   static constexpr int eBytes = 8 * N1h * 16 * 16;
   static constexpr int dBytes = nb * (B_ + 1) * 8;
-  static constexpr int pBytes = nb * nb * 4;      // symmetrised partner patch, staged per plane
-  static constexpr int offE = zBytes, offD = zBytes;   // D and P alias E (never live together)
-  static constexpr int offP = offD + s_al16(dBytes);
-  static constexpr int offTab = zBytes + s_al16(s_max(eBytes, s_al16(dBytes) + pBytes));
+  static constexpr int pBytes = nb * nb * 4;      // the partner's raw patch
+  static constexpr int offE = zBytes, offD = zBytes;   // D aliases E (never live together)
+  static constexpr int offTab = zBytes + s_al16(s_max(eBytes, dBytes));
   // tables (float offsets inside the table block)
   static constexpr int tPT = 0;
   static constexpr int tTW2 = tPT + N1w * nb * 4;
@@ -47,7 +46,16 @@ struct SCfg {
   static constexpr int tTWH = ((tTW3 + 3 * (B_ + 1) * 2) + 3) & ~3;   // 16-byte aligned for LDS.128
   static constexpr int tTWM = tTWH + N1h * twhPitch * 2;              // [N1w][16] float2: W_M^(c1 k2)
   static constexpr int tabBytes = s_al16((tTWM + N1w * 16 * 2) * 4);
-  static constexpr int smemBytes = offTab + tabBytes;
+  // Landing zone of the bulk-async (TMA) copy of the partner's patch: the 16-byte-aligned superset of the patch (a
+  // patch starts at any 4-byte boundary of the bank).  It lives in E behind D: E is idle between the forward and
+  // the inverse column passes, which is exactly when the patch is in flight and in use.  A dedicated 10 KB region
+  // would push two CTAs over the 196 KB shared-memory carve-out step and leave the L1 too small for the column
+  // loads in flight (measured: -6 % serial, -10 % pipelined).
+  static constexpr int prawBytes = s_al16(pBytes + 16);
+  static constexpr int offPraw = offD + s_al16(dBytes);
+  static_assert(s_al16(dBytes) + prawBytes <= eBytes, "D and the patch landing zone must fit inside E");
+  static constexpr int offBar = offTab + tabBytes;      // two mbarriers (tables, patch)
+  static constexpr int smemBytes = offBar + 16;
   static constexpr float invHW = (float)(1.0 / ((double)H_ * (double)W_));
   static_assert(H_ % 64 == 0 && W_ % 64 == 0, "static fused path needs H, W multiples of 64");
   static_assert(2 * B_ + 1 <= M && 2 * B_ + 1 <= H_, "band must fit the packed spectrum");
@@ -246,12 +254,35 @@ RD_HD void s_inv_fft8(const unsigned char* sm, int t, int par, cf (&pa)[8], cf (
   fft8<1>(pb);
 }
 
+// ---- epilogue policies ------------------------------------------------------------------------------
+// EpiClamp: y = clamp(x + d, lo, hi) * scale + shift, the caller epilogue as written (fundus.py:215,222-223,
+//           prostate.py:188); used when a clip bound is infinite.
+// EpiSat:   the same value for finite lo < hi in TWO instructions per pixel instead of four.  The band stage
+//           delivers d' = (d - lo... see fused_epilogue_sat()) so that  w = sat(x * a + d')  (one FFMA.SAT)
+//           is (clamp(x + d, lo, hi) - lo) / (hi - lo), and y = w * m + t with m = (hi - lo) * scale,
+//           t = lo * scale + shift.  Rounding differs from EpiClamp in the last bit only.
+RD_HD float rd_sat(float v) {
+#if defined(__CUDA_ARCH__)
+  return __saturatef(v);
+#else
+  return fminf(fmaxf(v, 0.f), 1.f);
+#endif
+}
+struct EpiClamp {
+  float lo, hi, scale, shift;
+  RD_HD float operator()(float x, float d) const { return fmaf(fminf(fmaxf(x + d, lo), hi), scale, shift); }
+};
+struct EpiSat {
+  float a, m, t;
+  RD_HD float operator()(float x, float d) const { return fmaf(rd_sat(fmaf(x, a, d)), m, t); }
+};
+
 // ---- inverse, second stage part 2: radix-2 combine of the two parities, add x, epilogue, store -----
 template <class CFG, int J>
 struct Combine {
   // `st(off, y, x)`: y is the augmented pixel quad, x the source quad just read (for the fused dual output)
-  template <class LoadF4, class StoreF4>
-  static RD_HD void run(LoadF4 ld, StoreF4 st, Epilogue ep, size_t base, const cf (&eva)[8], const cf (&evb)[8],
+  template <class LoadF4, class StoreF4, class EPI>
+  static RD_HD void run(LoadF4 ld, StoreF4 st, EPI ep, size_t base, const cf (&eva)[8], const cf (&evb)[8],
                         const cf (&oda)[8], const cf (&odb)[8]) {
     const cf wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
     const cf ea = eva[pos8(J)], eb = evb[pos8(J)];
@@ -260,11 +291,7 @@ struct Combine {
       const size_t off = base + (size_t)(CFG::N1h * (J + 8 * hi)) * CFG::M;
       const cf a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
       const float4 x = ld(off);
-      float4 y;
-      y.x = fmaf(fminf(fmaxf(x.x + a.re, ep.lo), ep.hi), ep.scale, ep.shift);
-      y.y = fmaf(fminf(fmaxf(x.y + bq.re, ep.lo), ep.hi), ep.scale, ep.shift);
-      y.z = fmaf(fminf(fmaxf(x.z + a.im, ep.lo), ep.hi), ep.scale, ep.shift);
-      y.w = fmaf(fminf(fmaxf(x.w + bq.im, ep.lo), ep.hi), ep.scale, ep.shift);
+      const float4 y = make_float4(ep(x.x, a.re), ep(x.y, bq.re), ep(x.z, a.im), ep(x.w, bq.im));
       st(off, y, x);
     }
     Combine<CFG, J + 1>::run(ld, st, ep, base, eva, evb, oda, odb);
@@ -272,15 +299,15 @@ struct Combine {
 };
 template <class CFG>
 struct Combine<CFG, 8> {
-  template <class LoadF4, class StoreF4>
-  static RD_HD void run(LoadF4, StoreF4, Epilogue, size_t, const cf (&)[8], const cf (&)[8], const cf (&)[8], const cf (&)[8]) {}
+  template <class LoadF4, class StoreF4, class EPI>
+  static RD_HD void run(LoadF4, StoreF4, EPI, size_t, const cf (&)[8], const cf (&)[8], const cf (&)[8], const cf (&)[8]) {}
 };
 
 // Variant with the x quads of rows J = 0..3 (both halves) preloaded one stage early (xpre[2 J + hi]).
 template <class CFG, int J>
 struct CombineP {
-  template <class LoadF4, class StoreF4>
-  static RD_HD void run(LoadF4 ld, StoreF4 st, Epilogue ep, size_t base, const float4 (&xpre)[8], const cf (&eva)[8],
+  template <class LoadF4, class StoreF4, class EPI>
+  static RD_HD void run(LoadF4 ld, StoreF4 st, EPI ep, size_t base, const float4 (&xpre)[8], const cf (&eva)[8],
                         const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
     const cf wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
     const cf ea = eva[pos8(J)], eb = evb[pos8(J)];
@@ -289,11 +316,7 @@ struct CombineP {
       const size_t off = base + (size_t)(CFG::N1h * (J + 8 * hi)) * CFG::M;
       const cf a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
       const float4 x = (J < 4) ? xpre[2 * (J & 3) + hi] : ld(off);
-      float4 y;
-      y.x = fmaf(fminf(fmaxf(x.x + a.re, ep.lo), ep.hi), ep.scale, ep.shift);
-      y.y = fmaf(fminf(fmaxf(x.y + bq.re, ep.lo), ep.hi), ep.scale, ep.shift);
-      y.z = fmaf(fminf(fmaxf(x.z + a.im, ep.lo), ep.hi), ep.scale, ep.shift);
-      y.w = fmaf(fminf(fmaxf(x.w + bq.im, ep.lo), ep.hi), ep.scale, ep.shift);
+      const float4 y = make_float4(ep(x.x, a.re), ep(x.y, bq.re), ep(x.z, a.im), ep(x.w, bq.im));
       st(off, y, x);
     }
     CombineP<CFG, J + 1>::run(ld, st, ep, base, xpre, eva, evb, oda, odb);
@@ -301,8 +324,8 @@ struct CombineP {
 };
 template <class CFG>
 struct CombineP<CFG, 8> {
-  template <class LoadF4, class StoreF4>
-  static RD_HD void run(LoadF4, StoreF4, Epilogue, size_t, const float4 (&)[8], const cf (&)[8], const cf (&)[8],
+  template <class LoadF4, class StoreF4, class EPI>
+  static RD_HD void run(LoadF4, StoreF4, EPI, size_t, const float4 (&)[8], const cf (&)[8], const cf (&)[8],
                         const cf (&)[8], const cf (&)[8]) {}
 };
 
@@ -313,15 +336,15 @@ RD_HD void s_inv_preload_x(LoadF4 ld, int strip, int t, float4 (&xpre)[8]) {
   for (int i = 0; i < 8; ++i) xpre[i] = ld(base + (size_t)(CFG::N1h * ((i >> 1) + 8 * (i & 1))) * CFG::M);
 }
 
-template <class CFG, class LoadF4, class StoreF4>
-RD_HD void s_inv_combine_store_pre(LoadF4 ld, StoreF4 st, Epilogue ep, int strip, int t, const float4 (&xpre)[8],
+template <class CFG, class LoadF4, class StoreF4, class EPI>
+RD_HD void s_inv_combine_store_pre(LoadF4 ld, StoreF4 st, EPI ep, int strip, int t, const float4 (&xpre)[8],
                                    const cf (&eva)[8], const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
   const size_t base = (size_t)(t >> 4) * CFG::M + strip * 16 + (t & 15);
   CombineP<CFG, 0>::run(ld, st, ep, base, xpre, eva, evb, oda, odb);
 }
 
-template <class CFG, class LoadF4, class StoreF4>
-RD_HD void s_inv_combine_store(LoadF4 ld, StoreF4 st, Epilogue ep, int strip, int t, const cf (&eva)[8],
+template <class CFG, class LoadF4, class StoreF4, class EPI>
+RD_HD void s_inv_combine_store(LoadF4 ld, StoreF4 st, EPI ep, int strip, int t, const cf (&eva)[8],
                                const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
   const size_t base = (size_t)(t >> 4) * CFG::M + strip * 16 + (t & 15);
   Combine<CFG, 0>::run(ld, st, ep, base, eva, evb, oda, odb);
@@ -431,19 +454,17 @@ RD_HD cf s_band_spectrum(const unsigned char* sm, int kh, int kw) {
   return f;
 }
 
-// stage the partner's patch, symmetrised over +-k, into shared memory: P[i] = (patch[i] + patch[n-1-i]) / 2
+// Band task of the mix kernel.  `patch` is the partner's raw [nb][nb] amplitude patch (shared memory on the device,
+// landed there by the bulk-async copy); Re(ifft2) only sees the +-k average, taken here on the fly.
+// `dc_add` is added to the DC bin of dF / (H W), i.e. to every pixel of delta (EpiSat's -lo / (hi - lo)).
 template <class CFG>
-RD_HD void s_stage_patch(unsigned char* sm, const float* patch, int i) {
-  constexpr int n = CFG::nb * CFG::nb;
-  reinterpret_cast<float*>(sm + CFG::offP)[i] = 0.5f * (patch[i] + patch[n - 1 - i]);
-}
-
-template <class CFG>
-RD_HD void s_band_mix(unsigned char* sm, float one_minus_ratio, int q) {
+RD_HD void s_band_mix(unsigned char* sm, const float* patch, float one_minus_ratio, float dc_add, int q) {
   const int khi = q % CFG::nb, kw = q / CFG::nb, kh = khi - CFG::b;
   if (kw == 0 && kh < 0) return;
   const cf f = s_band_spectrum<CFG>(sm, kh, kw);
-  const float at = reinterpret_cast<const float*>(sm + CFG::offP)[khi * CFG::nb + kw + CFG::b];
+  constexpr int n = CFG::nb * CFG::nb;
+  const int i = khi * CFG::nb + kw + CFG::b;
+  const float at = 0.5f * (patch[i] + patch[n - 1 - i]);
   const float a2 = f.re * f.re + f.im * f.im;
   cf d;
   if (a2 > 0.f) {
@@ -454,7 +475,10 @@ RD_HD void s_band_mix(unsigned char* sm, float one_minus_ratio, int q) {
   }
   float2* D = reinterpret_cast<float2*>(sm + CFG::offD);
   if (kw == 0) {
-    if (kh == 0) d.im = 0.f;
+    if (kh == 0) {
+      d.im = 0.f;
+      d.re += dc_add;
+    }
     D[(size_t)(CFG::nb - 1 - khi) * (CFG::b + 1)] = make_float2(d.re, -d.im);
   }
   D[(size_t)khi * (CFG::b + 1) + kw] = make_float2(d.re, d.im);

@@ -27,18 +27,22 @@ struct MixArgs {
   float* out;
   int B, C, H, W, b, n_bank, ratio_den;
   Epilogue ep;
-  bool independent = false;   // RAMDSIR_FLAG_INDEPENDENT
+  unsigned flags = 0;         // RAMDSIR_FLAG_*
   float* clean = nullptr;     // fused dual output (static fused kernels only): x * scale + shift
 };
 
 // fused single-CTA-per-plane path (ram_fused.cu)
 bool fused_supported(int H, int W, int b);
-void fused_set_variant(int v);
-bool fused_dual_supported(int H, int W, int b);
+bool fused_static_shape(int H, int W, int b);
+bool fused_dual_supported(int H, int W, int b, unsigned flags);
+int fused_prepare(int H, int W, int b);
+// the overlap bookkeeping of the static fused launches (ram_fused.cu) must forget a stream as soon as the library
+// enqueues anything else on it
+void fused_trail_reset(cudaStream_t st);
 int u8_to_f32(const unsigned char* x, float* y, size_t n, cudaStream_t st);
 int affine_f32(const float* x, float* y, size_t n, float scale, float shift, cudaStream_t st);
 int fused_mix(const MixArgs& a, cudaStream_t st);
-int fused_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, cudaStream_t st);
+int fused_bank(const float* imgs, float* bank, int N, int C, int H, int W, int b, unsigned flags, cudaStream_t st);
 // uint8 sources read directly by the static fused kernels (a.src is ignored)
 bool fused_u8_supported(int H, int W, int b);
 int fused_mix_u8(const MixArgs& a, const unsigned char* src, cudaStream_t st);

@@ -1,6 +1,7 @@
 // extern "C" surface of libramdsir.so (see include/ramdsir.h for the contract and the reference
 // interfaces each entry point replaces).
 #include <atomic>
+#include <cstdint>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -39,12 +40,15 @@ static int check_shape(int n, int C, int H, int W, int b) {
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool ranges_overlap(const void* a, size_t na, const void* b, size_t nb) {
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(a), b0 = reinterpret_cast<uintptr_t>(b);
+  return a0 < b0 + nb && b0 < a0 + na;
+}
 
-static std::atomic<int> g_force_path{0};
-
-static int path_of(int H, int W, int b) {
-  const int force = g_force_path.load(std::memory_order_relaxed);
-  if (force == RAMDSIR_PATH_GENERIC) return generic_supported(H, W, b) ? RAMDSIR_PATH_GENERIC : RAMDSIR_PATH_NONE;
+// Kernel family for a shape.  RAMDSIR_FLAG_PATH_GENERIC (a per-call flag, no global state) selects the generic
+// kernels explicitly so that two independent CUDA implementations can be cross-checked.
+static int path_of(int H, int W, int b, unsigned flags = 0) {
+  if (flags & RAMDSIR_FLAG_PATH_GENERIC) return generic_supported(H, W, b) ? RAMDSIR_PATH_GENERIC : RAMDSIR_PATH_NONE;
   if (fused_supported(H, W, b)) return RAMDSIR_PATH_FUSED;
   if (multipass_supported(H, W, b)) return RAMDSIR_PATH_MULTIPASS;
   if (generic_supported(H, W, b)) return RAMDSIR_PATH_GENERIC;
@@ -66,32 +70,30 @@ int ramdsir_band_halfwidth(int H, int W, double L) {
   return (int)std::floor(m * L);  // fundus.py:26, float64
 }
 
-int ramdsir_force_path(int path) {
-  if (path != 0 && path != RAMDSIR_PATH_GENERIC) {
-    set_error("force_path: only 0 (auto) or RAMDSIR_PATH_GENERIC can be forced");
-    return RAMDSIR_ERR_INVALID;
-  }
-  g_force_path.store(path, std::memory_order_relaxed);
-  return RAMDSIR_OK;
-}
-
-int ramdsir_set_fused_variant(int variant) {
-  if (variant < 0 || variant > 4 || variant == 3) {
-    set_error("set_fused_variant: 0 (auto), 1 (P2: one packed column per thread), 2 (runtime-shape kernel), 4 (x2: packed f32x2 arithmetic)");
-    return RAMDSIR_ERR_INVALID;
-  }
-  fused_set_variant(variant);
-  return RAMDSIR_OK;
-}
-
 int ramdsir_path(int C, int H, int W, int b) {
   if (check_shape(0, C, H, W, b)) return RAMDSIR_PATH_NONE;
   return path_of(H, W, b);
 }
 
-size_t ramdsir_workspace_bytes(int n_images, int C, int H, int W, int b) {
-  if (check_shape(n_images, C, H, W, b)) return 0;
+int ramdsir_prepare(int C, int H, int W, int b) {
+  int rc = check_shape(0, C, H, W, b);
+  if (rc) return rc;
   switch (path_of(H, W, b)) {
+    case RAMDSIR_PATH_FUSED: return fused_prepare(H, W, b);
+    case RAMDSIR_PATH_MULTIPASS:
+    case RAMDSIR_PATH_GENERIC: return RAMDSIR_OK;     // these build nothing lazily that blocks
+  }
+  set_error("no CUDA path for H=%d W=%d b=%d (and there is no CPU fallback)", H, W, b);
+  return RAMDSIR_ERR_UNSUPPORTED;
+}
+
+size_t ramdsir_workspace_bytes(int n_images, int C, int H, int W, int b) {
+  return ramdsir_workspace_bytes_ex(n_images, C, H, W, b, 0u);
+}
+
+size_t ramdsir_workspace_bytes_ex(int n_images, int C, int H, int W, int b, unsigned flags) {
+  if (check_shape(n_images, C, H, W, b)) return 0;
+  switch (path_of(H, W, b, flags)) {
     case RAMDSIR_PATH_GENERIC: return generic_workspace_bytes(n_images, C, H, W, b);
     case RAMDSIR_PATH_MULTIPASS: return multipass_workspace_bytes(n_images, C, H, W, b);
   }
@@ -100,6 +102,11 @@ size_t ramdsir_workspace_bytes(int n_images, int C, int H, int W, int b) {
 
 int ramdsir_bank_build_f32(const float* imgs_dev, float* bank_dev, int N, int C, int H, int W, int b,
                            void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return ramdsir_bank_build_f32_ex(imgs_dev, bank_dev, N, C, H, W, b, workspace_dev, workspace_bytes, stream, 0u);
+}
+
+int ramdsir_bank_build_f32_ex(const float* imgs_dev, float* bank_dev, int N, int C, int H, int W, int b,
+                              void* workspace_dev, size_t workspace_bytes, void* stream, unsigned flags) {
   int rc = check_shape(N, C, H, W, b);
   if (rc) return rc;
   if (N == 0) return RAMDSIR_OK;
@@ -107,15 +114,16 @@ int ramdsir_bank_build_f32(const float* imgs_dev, float* bank_dev, int N, int C,
     set_error("bank_build: null pointer");
     return RAMDSIR_ERR_INVALID;
   }
-  if (path_of(H, W, b) != RAMDSIR_PATH_GENERIC && !aligned16(imgs_dev)) {   // the float4 paths need 16-byte alignment
+  const int path = path_of(H, W, b, flags);
+  if (path != RAMDSIR_PATH_GENERIC && !aligned16(imgs_dev)) {   // the float4 paths need 16-byte alignment
     set_error("bank_build: imgs must be 16-byte aligned for this shape");
     return RAMDSIR_ERR_INVALID;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (path_of(H, W, b)) {
-    case RAMDSIR_PATH_FUSED: return fused_bank(imgs_dev, bank_dev, N, C, H, W, b, st);
-    case RAMDSIR_PATH_MULTIPASS: return multipass_bank(imgs_dev, bank_dev, N, C, H, W, b, workspace_dev, workspace_bytes, st);
-    case RAMDSIR_PATH_GENERIC: return generic_bank(imgs_dev, bank_dev, N, C, H, W, b, workspace_dev, workspace_bytes, st);
+  switch (path) {
+    case RAMDSIR_PATH_FUSED: return fused_bank(imgs_dev, bank_dev, N, C, H, W, b, flags, st);
+    case RAMDSIR_PATH_MULTIPASS: fused_trail_reset(st); return multipass_bank(imgs_dev, bank_dev, N, C, H, W, b, workspace_dev, workspace_bytes, st);
+    case RAMDSIR_PATH_GENERIC: fused_trail_reset(st); return generic_bank(imgs_dev, bank_dev, N, C, H, W, b, workspace_dev, workspace_bytes, st);
   }
   set_error("no CUDA path for H=%d W=%d b=%d (and there is no CPU fallback)", H, W, b);
   return RAMDSIR_ERR_UNSUPPORTED;
@@ -148,7 +156,8 @@ int ramdsir_mix_dual_f32(const float* src_dev, const float* bank_dev, const int6
     set_error("mix: null pointer");
     return RAMDSIR_ERR_INVALID;
   }
-  if (path_of(H, W, b) != RAMDSIR_PATH_GENERIC && (!aligned16(src_dev) || !aligned16(out_dev))) {
+  const int path = path_of(H, W, b, flags);
+  if (path != RAMDSIR_PATH_GENERIC && (!aligned16(src_dev) || !aligned16(out_dev))) {
     set_error("mix: src and out must be 16-byte aligned for this shape (float4 kernels)");
     return RAMDSIR_ERR_INVALID;
   }
@@ -156,30 +165,33 @@ int ramdsir_mix_dual_f32(const float* src_dev, const float* bank_dev, const int6
     set_error("mix: n_bank=%d ratio_den=%d must be positive", n_bank, ratio_den);
     return RAMDSIR_ERR_INVALID;
   }
-  if (src_dev == out_dev) {
-    set_error("mix: in-place operation is not supported (the source is read twice)");
+  const size_t batch_bytes = (size_t)B * C * H * W * sizeof(float);
+  if (ranges_overlap(src_dev, batch_bytes, out_dev, batch_bytes)) {
+    set_error("mix: out must not overlap src (the source is read twice)");
     return RAMDSIR_ERR_INVALID;
   }
   MixArgs a{src_dev, bank_dev, partner_idx_dev, ratio_k_dev, out_dev, B, C, H, W, b, n_bank, ratio_den,
             Epilogue{clip_lo, clip_hi, scale, shift}};
-  a.independent = (flags & RAMDSIR_FLAG_INDEPENDENT) != 0;
+  a.flags = flags;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (clean_out_dev) {
-    if ((path_of(H, W, b) != RAMDSIR_PATH_GENERIC && !aligned16(clean_out_dev)) || clean_out_dev == out_dev || clean_out_dev == src_dev) {
-      set_error("mix_dual: clean_out must be 16-byte aligned and distinct from src and out");
+    if ((path != RAMDSIR_PATH_GENERIC && !aligned16(clean_out_dev)) || ranges_overlap(clean_out_dev, batch_bytes, out_dev, batch_bytes) ||
+        ranges_overlap(clean_out_dev, batch_bytes, src_dev, batch_bytes)) {
+      set_error("mix_dual: clean_out must be 16-byte aligned and overlap neither src nor out");
       return RAMDSIR_ERR_INVALID;
     }
-    if (path_of(H, W, b) == RAMDSIR_PATH_FUSED && fused_dual_supported(H, W, b)) {
+    if (path == RAMDSIR_PATH_FUSED && fused_dual_supported(H, W, b, flags)) {
       a.clean = clean_out_dev;      // written by the RAM kernel itself, from the same read of src
     } else {
+      fused_trail_reset(st);
       rc = affine_f32(src_dev, clean_out_dev, (size_t)B * C * H * W, scale, shift, st);
       if (rc) return rc;
     }
   }
-  switch (path_of(H, W, b)) {
+  switch (path) {
     case RAMDSIR_PATH_FUSED: return fused_mix(a, st);
-    case RAMDSIR_PATH_MULTIPASS: return multipass_mix(a, workspace_dev, workspace_bytes, st);
-    case RAMDSIR_PATH_GENERIC: return generic_mix(a, workspace_dev, workspace_bytes, st);
+    case RAMDSIR_PATH_MULTIPASS: fused_trail_reset(st); return multipass_mix(a, workspace_dev, workspace_bytes, st);
+    case RAMDSIR_PATH_GENERIC: fused_trail_reset(st); return generic_mix(a, workspace_dev, workspace_bytes, st);
   }
   set_error("no CUDA path for H=%d W=%d b=%d (and there is no CPU fallback)", H, W, b);
   return RAMDSIR_ERR_UNSUPPORTED;
@@ -232,9 +244,16 @@ int ramdsir_mix_dual_u8(const uint8_t* src_dev, const float* bank_dev, const int
     set_error("mix_u8: uint8 sources are read directly only at 256x256/b=25 and 384x384/b=38 (got H=%d W=%d b=%d)", H, W, b);
     return RAMDSIR_ERR_UNSUPPORTED;
   }
+  const size_t out_bytes = (size_t)B * C * H * W * sizeof(float);
+  if (ranges_overlap(src_dev, out_bytes / 4, out_dev, out_bytes) ||
+      (clean_out_dev && (ranges_overlap(clean_out_dev, out_bytes, out_dev, out_bytes) ||
+                         ranges_overlap(clean_out_dev, out_bytes, src_dev, out_bytes / 4)))) {
+    set_error("mix_u8: src, out and clean_out must not overlap");
+    return RAMDSIR_ERR_INVALID;
+  }
   MixArgs a{nullptr, bank_dev, partner_idx_dev, ratio_k_dev, out_dev, B, C, H, W, b, n_bank, ratio_den,
             Epilogue{clip_lo, clip_hi, scale, shift}};
-  a.independent = (flags & RAMDSIR_FLAG_INDEPENDENT) != 0;
+  a.flags = flags;
   a.clean = clean_out_dev;
   return fused_mix_u8(a, src_dev, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -324,6 +343,9 @@ void ramdsir_pipe_destroy(ramdsir_pipe_t* p) {
 static int mix_host_impl(ramdsir_pipe_t* p, const float* src_host, const unsigned char* src_u8_host, const float* bank_dev,
                          const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host, int B,
                          int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift);
+static int mix_host_chunks(ramdsir_pipe_t* p, const float* src_host, const unsigned char* src_u8_host, const float* bank_dev,
+                           const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host, int B,
+                           int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift);
 
 int ramdsir_mix_host_f32(ramdsir_pipe_t* p, const float* src_host, const float* bank_dev,
                          const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host,
@@ -347,11 +369,30 @@ static int mix_host_impl(ramdsir_pipe_t* p, const float* src_host, const unsigne
     set_error("mix_host: invalid arguments");
     return RAMDSIR_ERR_INVALID;
   }
-  for (int i = 0; i < B; ++i)
+  for (int i = 0; i < B; ++i) {
     if (partner_idx_host[i] < 0 || partner_idx_host[i] >= n_bank) {
       set_error("mix_host: partner_idx[%d]=%lld outside the bank of %d images", i, (long long)partner_idx_host[i], n_bank);
       return RAMDSIR_ERR_INVALID;
     }
+    if (ratio_k_host[i] < 0 || ratio_k_host[i] > ratio_den) {
+      set_error("mix_host: ratio_k[%d]=%d outside [0, %d]", i, (int)ratio_k_host[i], ratio_den);
+      return RAMDSIR_ERR_INVALID;
+    }
+  }
+  const int rc_all = mix_host_chunks(p, src_host, src_u8_host, bank_dev, partner_idx_host, ratio_k_host, out_host, B, n_bank,
+                                     ratio_den, clip_lo, clip_hi, scale, shift);
+  // Success or failure, no copy may still be in flight on the caller's buffers when this returns.
+  int rc_sync = RAMDSIR_OK;
+  for (int i = 0; i < ramdsir_pipe::NSLOT; ++i) {
+    const cudaError_t e = cudaStreamSynchronize(p->st[i]);
+    if (e != cudaSuccess && rc_sync == RAMDSIR_OK && rc_all == RAMDSIR_OK) rc_sync = cuda_fail(e, "cudaStreamSynchronize(pipe stream)");
+  }
+  return rc_all ? rc_all : rc_sync;
+}
+
+static int mix_host_chunks(ramdsir_pipe_t* p, const float* src_host, const unsigned char* src_u8_host, const float* bank_dev,
+                           const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host, int B,
+                           int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale, float shift) {
   int slot = 0;
   for (int i0 = 0; i0 < B; i0 += p->chunk, slot = (slot + 1) % ramdsir_pipe::NSLOT) {
     const int n = (B - i0 < p->chunk) ? B - i0 : p->chunk;
@@ -379,7 +420,6 @@ static int mix_host_impl(ramdsir_pipe_t* p, const float* src_host, const unsigne
     if (rc) return rc;
     RD_CUDA(cudaMemcpyAsync(out_host + off, p->d_out[slot], bytes, cudaMemcpyDeviceToHost, st));
   }
-  for (int i = 0; i < ramdsir_pipe::NSLOT; ++i) RD_CUDA(cudaStreamSynchronize(p->st[i]));
   return RAMDSIR_OK;
 }
 

@@ -59,6 +59,8 @@ class HostPipeline:
         if not (isinstance(bank, torch.Tensor) and bank.is_cuda and bank.dtype == torch.float32 and bank.is_contiguous()
                 and tuple(bank.shape[1:]) == (self.C, nb, nb)):
             raise ValueError("bank must be a contiguous CUDA float32 tensor [N, %d, %d, %d]" % (self.C, nb, nb))
+        if bank.device != self.device:
+            raise ValueError("bank lives on %s, the pipeline on %s" % (bank.device, self.device))
         pidx = np.ascontiguousarray(np.asarray(partner_idx), dtype=np.int64)
         rk = np.ascontiguousarray(np.asarray(ratio_k), dtype=np.int32)
         if pidx.shape != (bsz,) or rk.shape != (bsz,):

@@ -70,7 +70,6 @@ def test_invalid_arguments_return_codes_not_crashes(lib):
     assert rc == _lib.ERR_INVALID and b"aligned" in lib.ramdsir_last_error()      # float4 kernels need 16-byte alignment
     rc = lib.ramdsir_bank_build_f32(None, None, 4, 3, 64, 64, 40, None, 0, None)
     assert rc == _lib.ERR_UNSUPPORTED
-    assert lib.ramdsir_force_path(7) == _lib.ERR_INVALID
 
 
 def test_uint8_entry_points_validate_without_gpu(lib):

@@ -1,7 +1,7 @@
 """CPU coverage of the CUDA kernels' index algebra.
 
 tools/emulate/emul_fused.cpp compiles the very same __host__ __device__ phase bodies the kernels call
-(ram_fused_core/static/p2/x2.cuh, ram_multipass.cuh) for the host and runs each CTA pipeline task by task with a
+(ram_fused_core/static.cuh, ram_multipass.cuh) for the host and runs each CTA pipeline task by task with a
 heap buffer standing in for shared memory.  Here every pipeline variant is checked against the numpy oracle, so
 a container without a GPU still validates twiddle tables, band indexing, packing and the butterfly stages.
 (The emulator is a test tool: it is never imported by the package and is not a fallback.)"""
@@ -29,7 +29,7 @@ def emu():
     F = ctypes.POINTER(ctypes.c_float)
     sig = [F, F, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int), ctypes.c_int, F] + \
           [ctypes.c_int] * 5 + [ctypes.c_float] * 4 + [F]
-    for name in ("emul_fused", "emul_fused_static", "emul_fused_p2", "emul_fused_x2", "emul_multipass"):
+    for name in ("emul_fused", "emul_fused_static", "emul_multipass"):
         getattr(lib, name).argtypes = sig
     return lib
 
@@ -54,10 +54,6 @@ CASES = [  # (entry point, C, H, W, integer-valued, constant plane?, bank tolera
     ("emul_fused", 1, 256, 256, True, False),
     ("emul_fused_static", 2, 256, 256, True, True),     # default kernels, incl. a constant plane
     ("emul_fused_static", 1, 384, 384, False, True),
-    ("emul_fused_p2", 1, 256, 256, True, True),
-    ("emul_fused_p2", 1, 384, 384, False, False),
-    ("emul_fused_x2", 2, 256, 256, True, True),
-    ("emul_fused_x2", 1, 384, 384, False, False),
     ("emul_multipass", 1, 512, 512, True, False),       # K2
 ]
 

@@ -44,19 +44,14 @@ def norm_epi_for(src):
     return O.FUNDUS_EPILOGUE if float(np.max(src)) > 2.0 else O.PROSTATE_EPILOGUE
 
 
-def gpu_mix(R, src_nchw, partners_nchw, pidx, rk, L, epi, force_generic=False):
-    from ramdsir_b200 import _lib
-    lib = _lib.load()
-    if force_generic:
-        _lib.check(lib.ramdsir_force_path(_lib.PATH_GENERIC))
-    try:
-        bank = R.build_amp_bank(dev(partners_nchw), L=L)
-        out = R.ram_mix_batch(dev(src_nchw), bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3])
-        torch.cuda.synchronize()
-        return out.cpu().numpy(), bank.cpu().numpy()
-    finally:
-        if force_generic:
-            lib.ramdsir_force_path(0)
+def gpu_mix(R, src_nchw, partners_nchw, pidx, rk, L, epi, force_generic=False, path=None):
+    """`path` ('generic' / 'runtime') selects another kernel family per call (RAMDSIR_FLAG_PATH_GENERIC /
+    RAMDSIR_FLAG_RUNTIME_SHAPE), so independent CUDA implementations can be compared."""
+    path = "generic" if force_generic else path
+    bank = R.build_amp_bank(dev(partners_nchw), L=L, path=path)
+    out = R.ram_mix_batch(dev(src_nchw), bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], path=path)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), bank.cpu().numpy()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -188,13 +183,10 @@ def test_constant_planes_take_phase_zero_like_the_reference(R, shape):
     check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "constant planes")
 
 
-@pytest.mark.parametrize("variant", [1, 2, 4], ids=["p2", "runtime", "x2"])
 @pytest.mark.parametrize("shape", [(3, 256, 256, True), (1, 384, 384, False)], ids=["fundus", "prostate"])
-def test_alternative_fused_variants(R, variant, shape):
-    """The other two implementations of the fused pipeline (selected through ramdsir_set_fused_variant)
-    meet the same tolerance and agree with the default kernels."""
-    from ramdsir_b200 import _lib
-    lib = _lib.load()
+def test_runtime_shape_kernel_agrees_with_static(R, shape):
+    """The runtime-shape implementation of the fused pipeline (RAMDSIR_FLAG_RUNTIME_SHAPE) meets the same tolerance
+    and agrees with the static kernels on the static shapes."""
     c, h, w, integer = shape
     rs = np.random.RandomState(23)
     lo, hi = (0, 255) if integer else (-1, 1)
@@ -203,13 +195,9 @@ def test_alternative_fused_variants(R, variant, shape):
     pidx, rk = rs.randint(0, 3, 5), np.array([1, 4, 7, 9, 10], np.int32)
     epi = O.FUNDUS_EPILOGUE if integer else O.PROSTATE_EPILOGUE
     base, bank0 = gpu_mix(R, src, par, pidx, rk, 0.1, epi)
-    _lib.check(lib.ramdsir_set_fused_variant(variant))
-    try:
-        got, bank = gpu_mix(R, src, par, pidx, rk, 0.1, epi)
-    finally:
-        lib.ramdsir_set_fused_variant(0)
-    check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "variant %d" % variant)
-    check(got, base, "variant %d vs default" % variant)
+    got, bank = gpu_mix(R, src, par, pidx, rk, 0.1, epi, path="runtime")
+    check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "runtime-shape kernel")
+    check(got, base, "runtime-shape vs static")
     assert O.rel_l2(bank, bank0) <= 1e-6
 
 
@@ -511,3 +499,79 @@ def test_uint8_sources_other_shapes_convert_on_device(R):
     assert rc == _lib.ERR_UNSUPPORTED and b"uint8" in lib.ramdsir_last_error()
     assert torch.equal(R.ram_mix_batch(src, bank, [0, 1, 0, 1], [1, 4, 7, 10]),
                        R.ram_mix_batch(src.float(), bank, [0, 1, 0, 1], [1, 4, 7, 10]))
+
+
+# ------------------------------------------------------------------------------------------------
+# (7) streams and the automatic overlap of consecutive launches
+def test_side_stream_orders_uploads_conversions_and_kernel(R):
+    """stream= makes the whole call (index upload, uint8 widening, RAM kernel) run on that stream: a side stream that
+    is NOT torch's current stream still produces the same bits as the default-stream call."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src8 = torch.randint(0, 256, (6, 3, 128, 128), device="cuda", generator=g, dtype=torch.uint8)   # widened on device
+    par = torch.rand(4, 3, 128, 128, device="cuda", generator=g) * 255
+    pidx, rk = [0, 1, 2, 3, 0, 1], [1, 3, 5, 7, 9, 10]
+    bank = R.build_amp_bank(par)
+    want = R.ram_mix_batch(src8, bank, pidx, rk, clip=(0.0, 255.0), scale=1 / 127.5, shift=-1.0)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        bank_s = R.build_amp_bank(par, stream=side)
+        got = R.ram_mix_batch(src8, bank_s, pidx, rk, clip=(0.0, 255.0), scale=1 / 127.5, shift=-1.0, stream=side)
+        side.synchronize()
+        assert torch.equal(got, want)
+
+
+def test_auto_overlap_keeps_stream_order_between_dependent_launches(R):
+    """Back-to-back launches overlap their tails only when their buffers are disjoint.  A chain in which every launch
+    reads what the previous one wrote (and a launch that overwrites the previous one's source) must give exactly the
+    strictly serial result; independent launches give it too."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, C, H, W = 64, 3, 256, 256
+    x0 = torch.rand(B, C, H, W, device="cuda", generator=g) * 255
+    bank = R.build_amp_bank(torch.rand(8, C, H, W, device="cuda", generator=g) * 255)
+    rs = np.random.RandomState(3)
+    pidx = torch.from_numpy(rs.randint(0, 8, B)).cuda()
+    rk = torch.from_numpy(rs.randint(1, 10, B).astype(np.int32)).cuda()
+
+    def chain(**kw):
+        a, b2 = torch.empty_like(x0), torch.empty_like(x0)
+        R.ram_mix_batch(x0, bank, pidx, rk, out=a, **kw)
+        R.ram_mix_batch(a, bank, pidx, rk, out=b2, **kw)      # reads what the previous launch wrote
+        R.ram_mix_batch(b2, bank, pidx, rk, out=a, **kw)      # overwrites the previous launch's source
+        R.ram_mix_batch(a, bank, pidx, rk, out=b2, **kw)
+        torch.cuda.synchronize()
+        return b2
+
+    want = chain(serial=True)
+    for _ in range(5):
+        assert torch.equal(chain(), want)
+    # independent batches: same bits with and without overlap, and a consumer right behind sees finished data
+    outs = [torch.empty_like(x0) for _ in range(4)]
+    for o in outs:
+        R.ram_mix_batch(x0, bank, pidx, rk, out=o)
+    sums = [o.double().sum() for o in outs]                   # torch kernels queued right behind the launches
+    ref = torch.empty_like(x0)
+    R.ram_mix_batch(x0, bank, pidx, rk, out=ref, serial=True)
+    torch.cuda.synchronize()
+    for o, s_ in zip(outs, sums):
+        assert torch.equal(o, ref) and s_.item() == ref.double().sum().item()
+
+
+def test_patch_staging_handles_unaligned_bank_rows(R):
+    """The partner's patch reaches shared memory through a 16-byte-granular bulk copy; bank rows start on arbitrary
+    4-byte boundaries (10 404 B per fundus patch) and the bank itself may be an odd slice of a gather buffer."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    C, H, W = 3, 256, 256
+    par = torch.rand(5, C, H, W, device="cuda", generator=g) * 255
+    src = torch.rand(10, C, H, W, device="cuda", generator=g) * 255
+    bank = R.build_amp_bank(par)
+    pidx, rk = [0, 1, 2, 3, 4, 4, 3, 2, 1, 0], [1, 2, 3, 4, 5, 6, 7, 8, 9, 1]
+    want = R.ram_mix_batch(src, bank, pidx, rk, clip=(0.0, 255.0), scale=1 / 127.5, shift=-1.0)
+    for shift_floats in (1, 2, 3):
+        buf = torch.empty(bank.numel() + 8, device="cuda")
+        view = buf[shift_floats:shift_floats + bank.numel()].view_as(bank)      # 4-, 8-, 12-byte misaligned bank
+        view.copy_(bank)
+        buf[shift_floats + bank.numel():] = float("nan")                        # anything read past the end shows up
+        buf[:shift_floats] = float("nan")
+        got = R.ram_mix_batch(src, view, pidx, rk, clip=(0.0, 255.0), scale=1 / 127.5, shift=-1.0)
+        assert torch.equal(got, want)

@@ -3,6 +3,7 @@
 // task, with a heap buffer standing in for shared memory, so the index algebra can be checked
 // against the numpy oracle in a container without a GPU.
 //   g++ -O2 -shared -fPIC -I ramdsir_b200/csrc tools/emulate/emul_fused.cpp -o tools/emulate/libemul.so
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -76,9 +77,9 @@ extern "C" int emul_fused(const float* src, const float* bank, const long long* 
 }
 
 // ---- static-shape (v2) pipeline ------------------------------------------------------------
-template <class CFG>
-static void run_plane_static(unsigned char* sm, const float* x, const float* patch, float omr, float* y,
-                             Epilogue ep, float* bank_out) {
+template <class CFG, class EPI>
+static void run_plane_static(unsigned char* sm, const float* x, const float* patch, float omr, float dc_add, float* y,
+                             EPI ep, float* bank_out) {
   CFG S;
   auto ld = [&](size_t off) { const float* p = x + 4 * off; return make_float4(p[0], p[1], p[2], p[3]); };
   auto st = [&](size_t off, float4 v, float4) { float* p = y + 4 * off; p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; };
@@ -98,8 +99,7 @@ static void run_plane_static(unsigned char* sm, const float* x, const float* pat
     for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) s_band_amp<CFG>(sm, bank_out, q);
     return;
   }
-  for (int i = 0; i < CFG::nb * CFG::nb; ++i) s_stage_patch<CFG>(sm, patch, i);
-  for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) s_band_mix<CFG>(sm, omr, q);
+  for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) s_band_mix<CFG>(sm, patch, omr, dc_add, q);
   for (int r = 0; r < CFG::nb * CFG::N1w; ++r) s_row_inv<CFG>(sm, r);
   (void)S;
   for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
@@ -128,9 +128,18 @@ static int run_all_static(const float* src, const float* bank, const long long* 
   for (int i = 0; i < B; ++i)
     for (int c = 0; c < C; ++c) {
       const size_t p = (size_t)i * C + c;
-      if (bank_out) { run_plane_static<CFG>(sm.data(), src + p * plane, nullptr, 0.f, nullptr, ep, bank_out + p * psz); continue; }
+      const EpiClamp ec{ep.lo, ep.hi, ep.scale, ep.shift};
+      if (bank_out) { run_plane_static<CFG>(sm.data(), src + p * plane, nullptr, 0.f, 0.f, nullptr, ec, bank_out + p * psz); continue; }
       const float omr = (float)(den - rk[i]) / (float)den;
-      run_plane_static<CFG>(sm.data(), src + p * plane, bank + ((size_t)pidx[i] * C + c) * psz, omr, out + p * plane, ep, nullptr);
+      const float* patch = bank + ((size_t)pidx[i] * C + c) * psz;
+      // finite clip range: the two-instruction saturating epilogue, exactly as launch_static() sets it up
+      if (std::isfinite(ep.lo) && std::isfinite(ep.hi) && ep.hi > ep.lo) {
+        const double span = (double)ep.hi - (double)ep.lo;
+        const EpiSat es{(float)(1.0 / span), (float)(span * (double)ep.scale), (float)((double)ep.lo * ep.scale + ep.shift)};
+        run_plane_static<CFG>(sm.data(), src + p * plane, patch, omr * es.a, (float)(-(double)ep.lo / span), out + p * plane, es, nullptr);
+      } else {
+        run_plane_static<CFG>(sm.data(), src + p * plane, patch, omr, 0.f, out + p * plane, ec, nullptr);
+      }
     }
   return 0;
 }
@@ -148,138 +157,6 @@ extern "C" int emul_fused_static_smem_bytes(int H, int W, int b) {
   if (H == 256 && W == 256 && b == 25) return SCfg<256, 256, 25>::smemBytes;
   if (H == 384 && W == 384 && b == 38) return SCfg<384, 384, 38>::smemBytes;
   return -1;
-}
-
-// ---- P2 pipeline (one packed column per thread) -------------------------------------------------
-template <class CFG>
-static void run_plane_p2(unsigned char* sm, const float* x, const float* patch, float omr, float* y, Epilogue ep,
-                         float* bank_out) {
-  auto ld = [&](size_t off) { return make_float2(x[2 * off], x[2 * off + 1]); };
-  auto st = [&](size_t off, float2 v) { y[2 * off] = v.x; y[2 * off + 1] = v.y; };
-  constexpr int NT = CFG::nthreads;
-  std::vector<cf> regs((size_t)NT * 16);
-  auto V = [&](int t) -> cf(&)[16] { return *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 16]); };
-  for (int strip = 0; strip < CFG::nstrips; ++strip) {
-    for (int t = 0; t < NT; ++t) p_f1_load_fft_tw<CFG>(ld, sm, strip, t, V(t));
-    for (int half = 0; half < 2; ++half) {
-      for (int t = 0; t < NT; ++t) p_f1_store_half<CFG>(sm, t, half, V(t));
-      for (int u = 0; u < 256; ++u) p_f1_pruned<CFG, 0>(sm, strip, half, u);
-      for (int u = 0; u < 256; ++u) p_f1_pruned<CFG, 1>(sm, strip, half, u);
-    }
-  }
-  for (int r = 0; r < CFG::nb * CFG::N1w; ++r) p_row_fwd<CFG>(sm, r);
-  if (bank_out) {
-    for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) p_band_amp<CFG>(sm, bank_out, q);
-    return;
-  }
-  for (int i = 0; i < CFG::nb * CFG::nb; ++i) s_stage_patch<CFG>(sm, patch, i);
-  for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) p_band_mix<CFG>(sm, omr, q);
-  for (int r = 0; r < CFG::nb * CFG::N1w; ++r) p_row_inv<CFG>(sm, r);
-  for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
-    for (int par = 0; par < 2; ++par) {
-      for (int u = 0; u < 256; ++u) p_inv_pruned<CFG, 0>(sm, strip, par, u);
-      for (int u = 0; u < 256; ++u) p_inv_pruned<CFG, 1>(sm, strip, par, u);
-      for (int t = 0; t < NT; ++t) p_inv_fft8<CFG>(sm, t, par, *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 16 + 8 * par]));
-    }
-    for (int t = 0; t < NT; ++t) {
-      cf* r = &regs[(size_t)t * 16];
-      p_inv_combine_store<CFG>(ld, st, ep, strip, t, *reinterpret_cast<cf(*)[8]>(r), *reinterpret_cast<cf(*)[8]>(r + 8));
-    }
-  }
-}
-
-template <class CFG>
-static int run_all_p2(const float* src, const float* bank, const long long* pidx, const int* rk, int den, float* out,
-                      int B, int C, Epilogue ep, float* bank_out) {
-  std::vector<unsigned char> sm(CFG::smemBytes);
-  fused_tables_fill_p2<CFG>(reinterpret_cast<float*>(sm.data() + CFG::offTab));
-  const size_t plane = (size_t)CFG::H * CFG::W, psz = (size_t)CFG::nb * CFG::nb;
-  for (int i = 0; i < B; ++i)
-    for (int c = 0; c < C; ++c) {
-      const size_t p = (size_t)i * C + c;
-      if (bank_out) { run_plane_p2<CFG>(sm.data(), src + p * plane, nullptr, 0.f, nullptr, ep, bank_out + p * psz); continue; }
-      const float omr = (float)(den - rk[i]) / (float)den;
-      run_plane_p2<CFG>(sm.data(), src + p * plane, bank + ((size_t)pidx[i] * C + c) * psz, omr, out + p * plane, ep, nullptr);
-    }
-  return 0;
-}
-
-extern "C" int emul_fused_p2(const float* src, const float* bank, const long long* pidx, const int* rk, int den,
-                             float* out, int B, int C, int H, int W, int b, float lo, float hi, float scale, float shift,
-                             float* bank_out) {
-  Epilogue ep{lo, hi, scale, shift};
-  if (H == 256 && W == 256 && b == 25) return run_all_p2<PCfg<256, 256, 25>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
-  if (H == 384 && W == 384 && b == 38) return run_all_p2<PCfg<384, 384, 38>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
-  return 1;
-}
-
-extern "C" int emul_fused_p2_smem_bytes(int H, int W, int b) {
-  if (H == 256 && W == 256 && b == 25) return PCfg<256, 256, 25>::smemBytes;
-  if (H == 384 && W == 384 && b == 38) return PCfg<384, 384, 38>::smemBytes;
-  return -1;
-}
-
-// ---- x2 pipeline (packed arithmetic) -------------------------------------------------------------
-template <class CFG>
-static void run_plane_x2(unsigned char* sm, const float* x, const float* patch, float omr, float* y, Epilogue ep,
-                         float* bank_out) {
-  auto ld = [&](size_t off) { const float* p = x + 4 * off; return make_float4(p[0], p[1], p[2], p[3]); };
-  auto st = [&](size_t off, float4 v, float4) { float* p = y + 4 * off; p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; };
-  constexpr int NT = CFG::nthreads;
-  std::vector<cf2> regs((size_t)NT * 16);
-  auto V = [&](int t) -> cf2(&)[16] { return *reinterpret_cast<cf2(*)[16]>(&regs[(size_t)t * 16]); };
-  for (int strip = 0; strip < CFG::nstrips; ++strip) {
-    for (int t = 0; t < NT; ++t) x_f1_load_fft_tw<CFG>(ld, sm, strip, t, V(t));
-    for (int half = 0; half < 2; ++half) {
-      for (int t = 0; t < NT; ++t) x_f1_store_half<CFG>(sm, t, half, V(t));
-      for (int u = 0; u < 128; ++u) x_f1_pruned<CFG, 0>(sm, strip, half, u);
-      for (int u = 0; u < 128; ++u) x_f1_pruned<CFG, 1>(sm, strip, half, u);
-    }
-  }
-  for (int r = 0; r < CFG::nb * CFG::N1w; ++r) x_row_fwd<CFG>(sm, r);
-  if (bank_out) {
-    for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) x_band_amp<CFG>(sm, bank_out, q);
-    return;
-  }
-  for (int i = 0; i < CFG::nb * CFG::nb; ++i) s_stage_patch<CFG>(sm, patch, i);
-  for (int q = 0; q < CFG::nb * (CFG::b + 1); ++q) x_band_mix<CFG>(sm, omr, q);
-  for (int r = 0; r < CFG::nb * CFG::N1w; ++r) x_row_inv<CFG>(sm, r);
-  for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
-    for (int par = 0; par < 2; ++par) {
-      for (int u = 0; u < 128; ++u) x_inv_pruned<CFG, 0>(sm, strip, par, u);
-      for (int u = 0; u < 128; ++u) x_inv_pruned<CFG, 1>(sm, strip, par, u);
-      for (int t = 0; t < NT; ++t) x_inv_fft8<CFG>(sm, t, par, *reinterpret_cast<cf2(*)[8]>(&regs[(size_t)t * 16 + 8 * par]));
-    }
-    for (int t = 0; t < NT; ++t) {
-      cf2* r = &regs[(size_t)t * 16];
-      x_inv_combine_store<CFG>(ld, st, ep, strip, t, *reinterpret_cast<cf2(*)[8]>(r), *reinterpret_cast<cf2(*)[8]>(r + 8));
-    }
-  }
-}
-
-template <class CFG>
-static int run_all_x2(const float* src, const float* bank, const long long* pidx, const int* rk, int den, float* out,
-                      int B, int C, Epilogue ep, float* bank_out) {
-  std::vector<unsigned char> sm(CFG::smemBytes);
-  fused_tables_fill_x2<CFG>(reinterpret_cast<float*>(sm.data() + CFG::offTab));
-  const size_t plane = (size_t)CFG::H * CFG::W, psz = (size_t)CFG::nb * CFG::nb;
-  for (int i = 0; i < B; ++i)
-    for (int c = 0; c < C; ++c) {
-      const size_t p = (size_t)i * C + c;
-      if (bank_out) { run_plane_x2<CFG>(sm.data(), src + p * plane, nullptr, 0.f, nullptr, ep, bank_out + p * psz); continue; }
-      const float omr = (float)(den - rk[i]) / (float)den;
-      run_plane_x2<CFG>(sm.data(), src + p * plane, bank + ((size_t)pidx[i] * C + c) * psz, omr, out + p * plane, ep, nullptr);
-    }
-  return 0;
-}
-
-extern "C" int emul_fused_x2(const float* src, const float* bank, const long long* pidx, const int* rk, int den,
-                             float* out, int B, int C, int H, int W, int b, float lo, float hi, float scale, float shift,
-                             float* bank_out) {
-  Epilogue ep{lo, hi, scale, shift};
-  if (H == 256 && W == 256 && b == 25) return run_all_x2<XCfg<256, 256, 25>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
-  if (H == 384 && W == 384 && b == 38) return run_all_x2<XCfg<384, 384, 38>>(src, bank, pidx, rk, den, out, B, C, ep, bank_out);
-  return 1;
 }
 
 // ---- multi-pass pipeline (K2) ---------------------------------------------------------------
