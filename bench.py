@@ -9,11 +9,16 @@ A "step" is one RAM pass over one batch of synthetic fundus-shaped images (BASEL
 every rank mixes its own 256-image shard against a bank that was built sharded and all-gathered once
 before the timed region.  One JSON line is printed by rank 0.
 
-value    = images/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+value    = images/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks).  The steps
+           rotate over distinct source batches and three output buffers, like a loader that keeps batches in flight;
+           the library overlaps the tail of one launch with the head of the next by itself when their buffers are
+           disjoint (include/ramdsir.h, "Overlap of consecutive launches"); "serial" is the same loop with that off.
 e2e      = images/s through the host-buffer C-ABI entry (ramdsir_mix_host_f32): pinned host src ->
            H2D -> kernel -> D2H -> pinned host out, every step, wall-clocked around the blocking call
 roofline = algorithmic bytes (2*C*H*W*4 + C*(2b+1)^2*4 per image) / measured kernel time
            against MEASURED_PEAKS.json's HBM copy bandwidth
+configs  = the other BASELINE.json configurations (prostate 512x1x384x384, hi-res 64x3x1024x1024, the 8192-image
+           batch of configs[3] sharded over the N ranks, the amplitude-bank builder), each with its own roofline
 cpu_baseline = the numpy oracle (a port of the reference's numpy path) on all host cores, bounded sample
 --impl reference = the same metric for the reference's CPU implementation (oracle port; the
            reference itself is Python under /root/reference and does not exist on the GPU box)
@@ -34,38 +39,41 @@ sys.path.insert(0, ROOT)
 
 SEED = 1337                       # reference default (train.py:60)
 L = 0.1
-# BASELINE.json configs[1] is the headline (default); the others are selectable for development runs.
+NSRC = 2                          # distinct source batches the timed steps rotate over
+NOUT = 3                          # rotating output buffers (a launch may overlap its predecessor, never the one before)
+CONFIG4_IMAGES = 8192             # BASELINE configs[3]: global batch, sharded over the ranks
+CONFIG4_BANK = 1024
+
 WORKLOADS = {
-    "fundus": dict(C=3, H=256, W=256, BATCH=256, N_BANK=768, N_DOMAINS=3, EPI="fundus", LO=0, HI=256,
+    "fundus": dict(C=3, H=256, W=256, BATCH=256, N_BANK=768, N_DOMAINS=3, EPI="fundus",
                    NAME="fundus RAM batch 256x3x256x256 fp32, L=0.1 (b=25), 3 source domains, clip[0,255]/127.5-1"),
-    "fundus1024": dict(C=3, H=256, W=256, BATCH=1024, N_BANK=768, N_DOMAINS=3, EPI="fundus", LO=0, HI=256,
-                       NAME="fundus RAM, per-rank shard of BASELINE configs[3] (8192 images / 8 GPUs): 1024x3x256x256 fp32, L=0.1"),
-    "prostate": dict(C=1, H=384, W=384, BATCH=512, N_BANK=640, N_DOMAINS=5, EPI="prostate", LO=-1, HI=1,
+    "prostate": dict(C=1, H=384, W=384, BATCH=512, N_BANK=640, N_DOMAINS=5, EPI="prostate",
                      NAME="prostate RAM batch 512x1x384x384 fp32, L=0.1 (b=38), 5 source domains, clip[-1,1]"),
-    "prostate3": dict(C=3, H=384, W=384, BATCH=128, N_BANK=320, N_DOMAINS=5, EPI="prostate", LO=-1, HI=1,
+    "prostate3": dict(C=3, H=384, W=384, BATCH=128, N_BANK=320, N_DOMAINS=5, EPI="prostate",
                       NAME="prostate RAM batch 128x3x384x384 fp32 (real 3-slice layout), L=0.1 (b=38), clip[-1,1]"),
-    "hires": dict(C=3, H=1024, W=1024, BATCH=64, N_BANK=48, N_DOMAINS=3, EPI="fundus", LO=0, HI=256,
+    "hires": dict(C=3, H=1024, W=1024, BATCH=64, N_BANK=48, N_DOMAINS=3, EPI="fundus",
                   NAME="high-res fundus RAM batch 64x3x1024x1024 fp32, L=0.1 (b=102), clip[0,255]/127.5-1"),
 }
-C, H, W = 3, 256, 256
-BATCH = 256                       # per GPU (configs[1])
-N_BANK = 768                      # source images in the amplitude bank (3 domains x 256; real fundus: 789)
-N_DOMAINS = 3
-NSRC = 2                          # distinct source batches the timed steps rotate over
-EPI_NAME, LO, HI = "fundus", 0, 256
-WORKLOAD = WORKLOADS["fundus"]["NAME"]
 
 
-def select_workload(name):
-    global C, H, W, BATCH, N_BANK, N_DOMAINS, WORKLOAD, EPI_NAME, LO, HI
-    w = WORKLOADS[name]
-    C, H, W, BATCH, N_BANK, N_DOMAINS = w["C"], w["H"], w["W"], w["BATCH"], w["N_BANK"], w["N_DOMAINS"]
-    WORKLOAD, EPI_NAME, LO, HI = w["NAME"], w["EPI"], w["LO"], w["HI"]
+class WL:
+    """One workload (shape, batch, bank, epilogue)."""
+
+    def __init__(self, name, batch=None, n_bank=None, label=None):
+        w = WORKLOADS[name]
+        self.key = name
+        self.C, self.H, self.W = w["C"], w["H"], w["W"]
+        self.BATCH = w["BATCH"] if batch is None else batch
+        self.N_BANK = w["N_BANK"] if n_bank is None else n_bank
+        self.N_DOMAINS = w["N_DOMAINS"]
+        self.EPI = w["EPI"]
+        self.NAME = w["NAME"] if label is None else label
 
 
-def synth(torch, shape, dev, gen):
+def synth(torch, wl, n, dev, gen):
     """Synthetic images: uint8-valued floats for fundus (fundus.py:212), uniform [-1, 1] for prostate."""
-    if EPI_NAME == "fundus":
+    shape = (n, wl.C, wl.H, wl.W)
+    if wl.EPI == "fundus":
         return torch.randint(0, 256, shape, device=dev, generator=gen).float()
     return torch.rand(shape, device=dev, generator=gen) * 2.0 - 1.0
 
@@ -74,16 +82,20 @@ def algorithmic_bytes_per_image(c, h, w, b):
     return 2 * c * h * w * 4 + c * (2 * b + 1) ** 2 * 4
 
 
+def bank_bytes_per_image(c, h, w, b):
+    return c * h * w * 4 + c * (2 * b + 1) ** 2 * 4
+
+
 def nominal_fft_flops_per_image(c, h, w):
     return c * 2 * 5 * h * w * np.log2(h * w)
 
 
-def draw_selection(batch, n_bank, seed):
+def draw_selection(wl, batch, seed):
     """Partner rows and ratio numerators with the reference's RNG calls (fundus.py:205,208,35)."""
     from ramdsir_b200 import rng
     rng.seed_worker_streams(seed)
-    per = n_bank // N_DOMAINS
-    names = ["Domain%d" % (i + 1) for i in range(N_DOMAINS)]
+    per = wl.N_BANK // wl.N_DOMAINS
+    names = ["Domain%d" % (i + 1) for i in range(wl.N_DOMAINS)]
     index = rng.BankIndex([(n, per) for n in names])
     sizes = {n: per for n in names}
     pidx = np.empty(batch, np.int64)
@@ -100,17 +112,19 @@ def draw_selection(batch, n_bank, seed):
 _CPU = {}
 
 
-def _cpu_init(seed):
+def _cpu_init(seed, key):
     from oracle import ram_oracle as O
+    wl = WL(key)
     rs = np.random.RandomState(seed)
     _CPU["O"] = O
-    if EPI_NAME == "fundus":
-        _CPU["src"] = rs.randint(0, 256, (8, C, H, W)).astype(np.float32)
-        _CPU["par"] = rs.randint(0, 256, (8, C, H, W)).astype(np.float32)
+    shape = (8, wl.C, wl.H, wl.W)
+    if wl.EPI == "fundus":
+        _CPU["src"] = rs.randint(0, 256, shape).astype(np.float32)
+        _CPU["par"] = rs.randint(0, 256, shape).astype(np.float32)
     else:
-        _CPU["src"] = (rs.rand(8, C, H, W) * 2 - 1).astype(np.float32)
-        _CPU["par"] = (rs.rand(8, C, H, W) * 2 - 1).astype(np.float32)
-    _CPU["epi"] = O.FUNDUS_EPILOGUE if EPI_NAME == "fundus" else O.PROSTATE_EPILOGUE
+        _CPU["src"] = (rs.rand(*shape) * 2 - 1).astype(np.float32)
+        _CPU["par"] = (rs.rand(*shape) * 2 - 1).astype(np.float32)
+    _CPU["epi"] = O.FUNDUS_EPILOGUE if wl.EPI == "fundus" else O.PROSTATE_EPILOGUE
 
 
 def cpu_model():
@@ -133,15 +147,15 @@ def _cpu_work(args):
     return float(y[0, 0, 0, 0])
 
 
-def cpu_images_per_s(n_images, cores, reps=1, precision="f64"):
+def cpu_images_per_s(wl, n_images, cores, reps=1, precision="f64"):
     """Images/s of the oracle on `cores` worker processes (the reference's DataLoader worker model,
     train.py:558-559); pool start-up excluded.  Returns (best img/s, list of per-rep seconds)."""
     import multiprocessing as mp
-    pidx, rk = draw_selection(n_images, N_BANK, SEED)
+    pidx, rk = draw_selection(wl, n_images, SEED)
     jobs = [(i, int(pidx[i]), int(rk[i]), precision) for i in range(n_images)]
     times = []
     if cores == 1:
-        _cpu_init(SEED)
+        _cpu_init(SEED, wl.key)
         for _ in range(reps):
             t0 = time.perf_counter()
             for j in jobs:
@@ -149,7 +163,7 @@ def cpu_images_per_s(n_images, cores, reps=1, precision="f64"):
             times.append(time.perf_counter() - t0)
     else:
         ctx = mp.get_context("fork")
-        with ctx.Pool(cores, initializer=_cpu_init, initargs=(SEED,)) as pool:
+        with ctx.Pool(cores, initializer=_cpu_init, initargs=(SEED, wl.key)) as pool:
             pool.map(_cpu_work, jobs[:cores])            # warm the workers
             for _ in range(reps):
                 t0 = time.perf_counter()
@@ -159,16 +173,19 @@ def cpu_images_per_s(n_images, cores, reps=1, precision="f64"):
 
 
 def run_reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path (oracle port) on all host cores, on OUR arm's config: every
+    step is the full 256-image batch of configs[1]."""
     if rank != 0:
         return
+    wl = WL(args.workload)
     cores = os.cpu_count() or 1
-    sample = max(cores * 4, 64)                           # images per step (bounded sample of the 256-image batch)
+    sample = wl.BATCH
     import multiprocessing as mp
-    pidx, rk = draw_selection(sample, N_BANK, SEED)
+    pidx, rk = draw_selection(wl, sample, SEED)
     jobs = [(i, int(pidx[i]), int(rk[i])) for i in range(sample)]
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(SEED,)) as pool:
-        for _ in range(max(args.warmup, 1)):
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(SEED, wl.key)) as pool:
+        for _ in range(max(min(args.warmup, 2), 1)):
             pool.map(_cpu_work, jobs, chunksize=max(1, sample // (cores * 4)))
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -179,8 +196,10 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": "RAM images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference numpy path (oracle port) on host cores; "
-                   "each step = %d images of the batch" % sample},
+        "config": {"workload": wl.NAME, "batch_per_gpu": wl.BATCH, "global_batch": wl.BATCH, "bank_images": wl.N_BANK,
+                   "seed": SEED,
+                   "note": "reference numpy path (oracle port of fundus.py:13-61 + caller epilogue) on the host cores of "
+                           "rank 0; each step = the full %d-image batch" % sample},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": "%d images/step x %d steps, float64 numpy path, multiprocessing.Pool(%d)"
                                    % (sample, args.steps, cores)},
@@ -247,12 +266,139 @@ def load_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic():
+def load_traffic(key="mix_fused_bytes_per_launch"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, or None."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["mix_fused_bytes_per_launch"]
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
     except Exception:
         return None
+
+
+def pin_to_cores(local_rank, world):
+    """Give every rank its own slice of the host cores (copy-engine feeding and the oracle pool stay off each other)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= world:
+            per = len(cores) // world
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
+class MixRun:
+    """Device-resident buffers of one workload on this rank + the timed loops over them."""
+
+    def __init__(self, torch, R, sharded, dist, wl, dev, rank, world, nsrc=NSRC, nout=NOUT):
+        self.torch, self.R, self.wl, self.dev, self.rank, self.world, self.dist = torch, R, wl, dev, rank, world, dist
+        self.b = R.band_halfwidth(wl.H, wl.W, L)
+        g = torch.Generator(device=dev).manual_seed(SEED + rank)
+        self.srcs = [synth(torch, wl, wl.BATCH, dev, g) for _ in range(nsrc)]
+        self.outs = [torch.empty_like(self.srcs[0]) for _ in range(nout)]
+        # amplitude bank: built sharded (each rank its rows), replicated once by an all-gather
+        lo, hi = sharded.shard_range(wl.N_BANK, rank, world)
+        gb = torch.Generator(device=dev).manual_seed(SEED * 7 + 1 + 1000 * rank)
+        self.bank_imgs = synth(torch, wl, hi - lo, dev, gb)
+        self.sharded = sharded
+        self.bank = None
+        self.pidx_h, self.rk_h = draw_selection(wl, wl.BATCH, SEED + rank)
+        self.pidx, self.rk = torch.from_numpy(self.pidx_h).to(dev), torch.from_numpy(self.rk_h).to(dev)
+        self.epi = R.FUNDUS_EPILOGUE if wl.EPI == "fundus" else R.PROSTATE_EPILOGUE
+        self.i = 0
+
+    def _sync(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def build_bank(self):
+        """Cold first call (tables, allocator, NCCL connect) is discarded; the timed calls are warm.  Returns
+        (kernel-only ms of this rank's shard, ms of build + all-gather, max over ranks done by the caller)."""
+        torch = self.torch
+        wl = self.wl
+        self.bank = self.sharded.build_amp_bank_sharded(self.bank_imgs, wl.N_BANK, L)      # cold
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best_k = best_all = 1e9
+        local = torch.empty((self.bank_imgs.shape[0], wl.C, 2 * self.b + 1, 2 * self.b + 1), device=self.dev)
+        for _ in range(3):
+            self._sync()
+            e0.record()
+            self.R.build_amp_bank(self.bank_imgs, L, out=local)
+            e1.record()
+            torch.cuda.synchronize()
+            best_k = min(best_k, e0.elapsed_time(e1))
+            self._sync()
+            e0.record()
+            self.bank = self.sharded.build_amp_bank_sharded(self.bank_imgs, wl.N_BANK, L)
+            e1.record()
+            torch.cuda.synchronize()
+            best_all = min(best_all, e0.elapsed_time(e1))
+        del local
+        return best_k, best_all
+
+    def bank_bit_identical(self):
+        """Rebuild the WHOLE bank on this rank from all ranks' source images and compare with the gathered one."""
+        torch, wl = self.torch, self.wl
+        parts = []
+        for r in range(self.world):
+            lo, hi = self.sharded.shard_range(wl.N_BANK, r, self.world)
+            gb = torch.Generator(device=self.dev).manual_seed(SEED * 7 + 1 + 1000 * r)
+            parts.append(self.R.build_amp_bank(synth(torch, wl, hi - lo, self.dev, gb), L))
+        ok = bool(torch.equal(torch.cat(parts, 0), self.bank))
+        t = torch.tensor([1 if ok else 0], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def step(self, srcs=None, **kw):
+        i = self.i
+        self.i += 1
+        ss = self.srcs if srcs is None else srcs
+        e = self.epi
+        self.R.ram_mix_batch(ss[i % len(ss)], self.bank, self.pidx, self.rk, L=L, clip=e[:2], scale=e[2], shift=e[3],
+                             out=self.outs[i % len(self.outs)], **kw)
+
+    def timed(self, steps, warmup, srcs=None, **kw):
+        """ms per step on this rank (CUDA events on the launching stream), after `warmup` untimed steps."""
+        torch = self.torch
+        for _ in range(warmup):
+            self.step(srcs, **kw)
+        self._sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.step(srcs, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        return e0.elapsed_time(e1) / steps
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def free(self):
+        self.srcs = self.outs = self.bank = self.bank_imgs = None
+        self.torch.cuda.empty_cache()
+
+
+def config_line(run, ms_rank, ms_max, peak, serial_ms=None, extra=None):
+    wl = run.wl
+    ab = algorithmic_bytes_per_image(wl.C, wl.H, wl.W, run.b) * wl.BATCH
+    ach = ab / (ms_rank * 1e-3) / 1e9
+    d = {"workload": wl.NAME, "batch_per_gpu": wl.BATCH, "value": wl.BATCH * run.world / (ms_max * 1e-3), "unit": "images/s",
+         "ms_per_step": ms_max,
+         "kernel_path": {1: "fused", 2: "multipass", 3: "generic"}.get(run.R.kernel_path(wl.C, wl.H, wl.W, run.b)),
+         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                      "algorithmic_bytes_per_launch": ab, "kernel_ms": ms_rank}}
+    if serial_ms is not None:
+        d["serial"] = {"ms_per_step": serial_ms, "frac": ab / (serial_ms * 1e-3) / 1e9 / peak}
+    if extra:
+        d.update(extra)
+    return d
 
 
 def run_ours(args, rank, local_rank, world):
@@ -262,190 +408,184 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback). Use --impl reference for the CPU arm.")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_cores = pin_to_cores(local_rank, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import ramdsir_b200 as R
     from ramdsir_b200 import _lib, sharded
     from ramdsir_b200.host import HostPipeline
 
-    b = R.band_halfwidth(H, W, L)
-    g = torch.Generator(device=dev).manual_seed(SEED + rank)
-    # A loader pipeline keeps several batches in flight: consecutive steps read DIFFERENT source batches (so no step
-    # finds its input in L2 because the previous step just read it) and write one of three rotating output buffers.
-    srcs = [synth(torch, (BATCH, C, H, W), dev, g) for _ in range(NSRC)]
-    src = srcs[0]
-    outs = [torch.empty_like(src) for _ in range(3)]
-    out = outs[0]
+    peak, peak_src = load_peak()
+    wl = WL(args.workload)
+    W = max(args.warmup, 3)
+    run = MixRun(torch, R, sharded, dist, wl, dev, rank, world)
+    b = run.b
+    bank_kernel_ms, bank_all_ms = run.build_bank()
+    bank_kernel_ms, bank_all_ms = run.max_over_ranks(bank_kernel_ms), run.max_over_ranks(bank_all_ms)
+    bank_same = run.bank_bit_identical() if world > 1 else None
 
-    # amplitude bank: built sharded (each rank its rows), replicated once by an all-gather
-    lo, hi = sharded.shard_range(N_BANK, rank, world)
-    gb = torch.Generator(device=dev).manual_seed(SEED * 7 + 1)
-    bank_src_all = None
-    torch.cuda.synchronize()
-    bank_imgs = synth(torch, (hi - lo, C, H, W), dev, gb)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    bank = sharded.build_amp_bank_sharded(bank_imgs, N_BANK, L)
-    e1.record()
-    torch.cuda.synchronize()
-    bank_ms = e0.elapsed_time(e1)
-    del bank_imgs, bank_src_all
-
-    pidx_h, rk_h = draw_selection(BATCH, N_BANK, SEED + rank)
-    pidx, rk = torch.from_numpy(pidx_h).to(dev), torch.from_numpy(rk_h).to(dev)
-    epi = R.FUNDUS_EPILOGUE if EPI_NAME == "fundus" else R.PROSTATE_EPILOGUE
-
-    # Steps are independent batches (own output buffer each), as in a loader pipeline that keeps two
-    # batches in flight: the launch is flagged RAMDSIR_FLAG_INDEPENDENT so it may start on SMs that the
-    # previous launch has already vacated (--serial disables that).
-    state = {"i": 0}
-
-    def step():
-        i = state["i"]
-        state["i"] += 1
-        R.ram_mix_batch(srcs[i % NSRC], bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=outs[i % 3],
-                        serial=args.serial)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
+    # ---- headline: K steps, device-resident, automatic tail overlap (or --serial) ----
+    for _ in range(W):
+        run.step(serial=args.serial)
+    run._sync()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     launches0 = _lib.launch_count()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
+    ms = run.timed(args.steps, 0, serial=args.serial)
     launches = _lib.launch_count() - launches0
-    # the same K steps with plain stream-ordered launches (reported next to the headline for transparency)
-    serial_ms = None
-    if not args.serial:
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(args.steps):
-            R.ram_mix_batch(srcs[i % NSRC], bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=outs[i % 3],
-                            serial=True)
-        e1.record()
-        torch.cuda.synchronize()
-        serial_ms = e0.elapsed_time(e1) / args.steps
+    ms_max = run.max_over_ranks(ms)
+    value = wl.BATCH * world / (ms_max * 1e-3)
+    serial_ms = None if args.serial else run.timed(args.steps, 2, serial=True)
+
     # uint8-resident sources (what a fundus loader actually holds, fundus.py:205-214): the kernel reads the bytes
     # itself, 5 instead of 8 algorithmic bytes per pixel.  Same K steps, same launch mode; reported beside the headline.
     u8_src = None
-    if EPI_NAME == "fundus" and R.u8_supported(C, H, W, b):
-        src_u8d = src.to(torch.uint8)
-        o8 = outs                                   # reuse the rotating output buffers
-        want0 = torch.empty_like(src)
-        R.ram_mix_batch(src, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=want0, serial=True)
-        for i in range(3):
-            R.ram_mix_batch(src_u8d, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=o8[i % 3],
-                            serial=args.serial)
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(args.steps):
-            R.ram_mix_batch(src_u8d, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=o8[i % 3],
-                            serial=args.serial)
-        e1.record()
-        torch.cuda.synchronize()
-        u8_ms = e0.elapsed_time(e1) / args.steps
-        u8_bytes = (C * H * W * 5 + C * (2 * b + 1) ** 2 * 4) * BATCH
-        u8_src = {"value": BATCH / (u8_ms * 1e-3), "unit": "images/s", "ms_per_step": u8_ms,
+    if wl.EPI == "fundus" and R.u8_supported(wl.C, wl.H, wl.W, b):
+        s8 = [s.to(torch.uint8) for s in run.srcs]
+        want0 = torch.empty_like(run.srcs[0])
+        e = run.epi
+        R.ram_mix_batch(run.srcs[0], run.bank, run.pidx, run.rk, L=L, clip=e[:2], scale=e[2], shift=e[3], out=want0, serial=True)
+        got0 = torch.empty_like(want0)
+        R.ram_mix_batch(s8[0], run.bank, run.pidx, run.rk, L=L, clip=e[:2], scale=e[2], shift=e[3], out=got0, serial=True)
+        u8_ms = run.timed(args.steps, 3, srcs=s8, serial=args.serial)
+        u8_bytes = (wl.C * wl.H * wl.W * 5 + wl.C * (2 * b + 1) ** 2 * 4) * wl.BATCH
+        u8_src = {"value": wl.BATCH / (u8_ms * 1e-3), "unit": "images/s", "ms_per_step": u8_ms,
                   "algorithmic_bytes_per_launch": u8_bytes, "achieved": u8_bytes / (u8_ms * 1e-3) / 1e9,
-                  "bit_identical_to_f32_source": bool(torch.equal(o8[0], want0)),
+                  "bit_identical_to_f32_source": bool(torch.equal(got0, want0)),
                   "note": "rank 0; ramdsir_mix_dual_u8: sources resident in HBM as uint8 [B,C,H,W], float32 output"}
-        del src_u8d, o8, want0
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
-    value = BATCH * world / (ms_per_step * 1e-3)
+        del s8, want0, got0
 
-    # end-to-end through the host-buffer C-ABI entry (pinned host -> device -> pinned host)
-    src_h = src.cpu().pin_memory()
+    # ---- end-to-end through the host-buffer C-ABI entry (pinned host -> device -> pinned host) ----
+    src_h = run.srcs[0].cpu().pin_memory()
     out_h = torch.empty_like(src_h).pin_memory()
     e2e_steps = 1 if args.no_e2e else max(3, min(args.steps, 30))
-    with HostPipeline(chunk_images=max(1, BATCH // 8), C=C, H=H, W=W, L=L) as pipe:
+    chunk = args.e2e_chunk or max(1, min(32, wl.BATCH))          # 32-image chunks measured best (tools/e2e_chunks.py)
+    e2e_u8 = None
+    link = None
+    with HostPipeline(chunk_images=chunk, C=wl.C, H=wl.H, W=wl.W, L=L) as pipe:
         for _ in range(3):
-            pipe.mix(src_h, bank, pidx_h, rk_h, out_h, epilogue=epi)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            pipe.mix(src_h, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
+        run._sync()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            pipe.mix(src_h, bank, pidx_h, rk_h, out_h, epilogue=epi)
+            pipe.mix(src_h, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
         e2e_s = time.perf_counter() - t0
+        e = run.epi
+        R.ram_mix_batch(run.srcs[0], run.bank, run.pidx, run.rk, L=L, clip=e[:2], scale=e[2], shift=e[3], out=run.outs[0], serial=True)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(out_h, run.outs[0].cpu()))
         # same leg with uint8 host images (what a fundus loader holds, fundus.py:212): H2D bytes / 4
-        e2e_u8 = None
-        if EPI_NAME == "fundus":
+        if wl.EPI == "fundus":
             src_u8 = src_h.to(torch.uint8).pin_memory()
             for _ in range(2):
-                pipe.mix(src_u8, bank, pidx_h, rk_h, out_h, epilogue=epi)
-            torch.cuda.synchronize()
+                pipe.mix(src_u8, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
+            run._sync()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                pipe.mix(src_u8, bank, pidx_h, rk_h, out_h, epilogue=epi)
-            e2e_u8 = BATCH * e2e_steps / (time.perf_counter() - t0)
-    R.ram_mix_batch(src, bank, pidx, rk, L=L, clip=epi[:2], scale=epi[2], shift=epi[3], out=outs[0], serial=True)
-    torch.cuda.synchronize()
-    same = bool(torch.equal(out_h, outs[0].cpu()))
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = BATCH * world * e2e_steps / float(t.item())
+                pipe.mix(src_u8, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
+            e2e_u8 = wl.BATCH * world * e2e_steps / run.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = wl.BATCH * world * e2e_steps / run.max_over_ranks(e2e_s)
+    if not args.no_e2e:
+        # what the host link gives this rank while every rank copies at once: the ceiling of any host-buffer path
+        d_in, d_out = run.srcs[0], run.outs[0]
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        run._sync()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            with torch.cuda.stream(s1):
+                d_in.copy_(src_h, non_blocking=True)
+            with torch.cuda.stream(s2):
+                out_h.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = run.max_over_ranks(time.perf_counter() - t0)
+        gbs = 3 * src_h.numel() * 4 / dt / 1e9
+        link = {"h2d_gbs_per_rank": gbs, "d2h_gbs_per_rank": gbs,
+                "ceiling_images_per_s": wl.BATCH * world * 3 / dt,
+                "note": "pinned host <-> device copies of one batch each way, both directions at once, all ranks at once; "
+                        "ceiling = the rate at which batches can cross the host link at all"}
     clocks = sampler.stop() if sampler else None
 
+    # ---- the other BASELINE configurations, each a few steps ----
+    configs = {}
+    if not args.no_configs:
+        ksteps = max(5, min(args.steps, 40))
+        configs["bank_builder_" + wl.key] = {
+            "workload": "amplitude-bank builder (K3), %d source images of the %s shape per rank, warm" % (run.bank_imgs.shape[0], wl.key),
+            "kernel_ms": bank_kernel_ms, "build_plus_allgather_ms": bank_all_ms,
+            "value": run.bank_imgs.shape[0] * world / (bank_kernel_ms * 1e-3), "unit": "images/s",
+            "roofline": (lambda ab: {"bound": "hbm", "achieved": ab / (bank_kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": ab / (bank_kernel_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": ab})(
+                bank_bytes_per_image(wl.C, wl.H, wl.W, b) * run.bank_imgs.shape[0])}
+        run.free()
+        extra = [("prostate_512x1x384x384", WL("prostate")), ("hires_64x3x1024x1024", WL("hires")),
+                 ("config4_8192_fundus_sharded", WL("fundus", batch=(CONFIG4_IMAGES + world - 1) // world, n_bank=CONFIG4_BANK,
+                                                    label="BASELINE configs[3]: %d fundus images batch-sharded over %d rank(s), "
+                                                          "bank of %d source images built sharded + all-gathered"
+                                                          % (CONFIG4_IMAGES, world, CONFIG4_BANK)))]
+        for key, w2 in extra:
+            if w2.key == args.workload and w2.BATCH == wl.BATCH:
+                continue
+            r2 = MixRun(torch, R, sharded, dist, w2, dev, rank, world)
+            bk, ball = r2.build_bank()
+            bk, ball = r2.max_over_ranks(bk), r2.max_over_ranks(ball)
+            same2 = r2.bank_bit_identical() if (world > 1 and key.startswith("config4")) else None
+            m = r2.timed(ksteps, 3)
+            ms2 = r2.timed(ksteps, 2, serial=True)
+            x = {"steps": ksteps, "bank_images": w2.N_BANK, "bank_kernel_ms": bk, "bank_build_plus_allgather_ms": ball}
+            if same2 is not None:
+                x["bank_bit_identical"] = same2
+            configs[key] = config_line(r2, m, r2.max_over_ranks(m), peak, serial_ms=ms2, extra=x)
+            r2.free()
+            del r2
+
     if rank == 0:
-        peak, peak_src = load_peak()
-        abytes = algorithmic_bytes_per_image(C, H, W, b) * BATCH
-        kernel_s = (ms / args.steps) * 1e-3                     # rank 0's own launches, one kernel per step
+        abytes = algorithmic_bytes_per_image(wl.C, wl.H, wl.W, b) * wl.BATCH
+        kernel_s = ms * 1e-3                                       # rank 0's own launches, one kernel per step
         achieved = abytes / kernel_s / 1e9
         line = {
             "metric": "RAM images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "bank_images": N_BANK,
-                       "bank_build_allgather_ms": bank_ms, "seed": SEED,
-                       "l2": "inputs %.0f MB + outputs %.0f MB per step exceed the 126 MB L2 (no flush needed)"
-                             % (src.numel() * 4 / 1e6, src.numel() * 4 / 1e6),
+            "config": {"workload": wl.NAME, "batch_per_gpu": wl.BATCH, "global_batch": wl.BATCH * world, "bank_images": wl.N_BANK,
+                       "bank_build_allgather_ms": bank_all_ms, "bank_kernel_ms": bank_kernel_ms, "seed": SEED,
+                       "l2": "steps rotate over %d source batches (%.0f MB each) and %d output buffers (%.0f MB each): far "
+                             "beyond the 126 MB L2, no step finds its input cached by the previous one (no flush needed)"
+                             % (NSRC, wl.BATCH * wl.C * wl.H * wl.W * 4 / 1e6, NOUT, wl.BATCH * wl.C * wl.H * wl.W * 4 / 1e6),
                        "parallelism": "batch-sharded x%d, bank all-gather once" % world,
                        "launch_overlap": "off (--serial)" if args.serial else
-                       "consecutive steps are independent batches (alternating output buffers) launched with "
-                       "RAMDSIR_FLAG_INDEPENDENT: a step may start on SMs the previous step has vacated",
-                       "kernel_path": {1: "fused", 2: "multipass", 3: "generic"}.get(R.kernel_path(C, H, W, b))},
+                       "automatic: the library overlaps a launch with the tail of the previous one when their buffers are "
+                       "disjoint (no flag from the caller); the later launch never completes before the earlier one",
+                       "host_cores_per_rank": host_cores,
+                       "kernel_path": {1: "fused", 2: "multipass", 3: "generic"}.get(R.kernel_path(wl.C, wl.H, wl.W, b))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes, "kernel_ms": kernel_s * 1e3},
             "serial": None if serial_ms is None else {
-                "ms_per_step": serial_ms, "value": BATCH / (serial_ms * 1e-3),
+                "ms_per_step": serial_ms, "value": wl.BATCH / (serial_ms * 1e-3),
                 "frac": abytes / (serial_ms * 1e-3) / 1e9 / peak,
-                "note": "rank 0, same K steps launched strictly stream-ordered (no overlap between steps)"},
+                "note": "rank 0, same K steps with RAMDSIR_FLAG_SERIAL (no overlap between steps)"},
             "u8_source": None if u8_src is None else dict(u8_src, frac=u8_src["achieved"] / peak),
-            "fft_tflops_nominal": nominal_fft_flops_per_image(C, H, W) * value / 1e12,
+            "fft_tflops_nominal": nominal_fft_flops_per_image(wl.C, wl.H, wl.W) * value / 1e12,
             "e2e": {"value": e2e_value, "unit": "images/s",
-                    "h2d_bytes_per_step": int(src_h.numel() * 4 + pidx_h.nbytes + rk_h.nbytes),
-                    "d2h_bytes_per_step": int(out_h.numel() * 4), "steps": e2e_steps,
-                    "matches_device_path": same, "timing": "wall clock around the blocking C-ABI call",
+                    "h2d_bytes_per_step": int(src_h.numel() * 4 + run.pidx_h.nbytes + run.rk_h.nbytes),
+                    "d2h_bytes_per_step": int(out_h.numel() * 4), "steps": e2e_steps, "chunk_images": chunk,
+                    "matches_device_path": same, "timing": "wall clock around the blocking C-ABI call, max over ranks",
                     "uint8_input_value": e2e_u8,
-                    "uint8_input_note": "rank 0, same call with uint8 host images (ramdsir_mix_host_u8): H2D bytes / 4"},
+                    "uint8_input_note": "same call with uint8 host images (ramdsir_mix_host_u8): H2D bytes / 4",
+                    "host_link": link},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if bank_same is not None:
+            line["bank_bit_identical"] = bank_same
+        if configs:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            n = max(64, cores * 8)
-            ips, times = cpu_images_per_s(n, cores, reps=2)
-            ips1, _ = cpu_images_per_s(16, 1, reps=1)
-            ips32, _ = cpu_images_per_s(n, cores, reps=1, precision="native")
+            n = wl.BATCH
+            ips, times = cpu_images_per_s(wl, n, cores, reps=2)
+            ips1, _ = cpu_images_per_s(wl, 16, 1, reps=1)
+            ips32, _ = cpu_images_per_s(wl, n, cores, reps=1, precision="native")
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": "%d images of the workload x2 reps (best), float64 numpy path, "
+                                    "sample": "the %d-image batch x2 reps (best), float64 numpy path, "
                                               "multiprocessing.Pool(%d)" % (n, cores),
                                     "single_core_images_per_s": ips1,
                                     "native_float32_path_images_per_s": ips32,   # what numpy >= 2 does with float32 input
@@ -462,11 +602,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--serial", action="store_true", help="plain stream-ordered launches (no overlap between steps)")
+    ap.add_argument("--serial", action="store_true", help="RAMDSIR_FLAG_SERIAL on every step (no overlap between steps)")
     ap.add_argument("--no-e2e", action="store_true", help="(dev) shorten the host-buffer end-to-end leg to one step")
+    ap.add_argument("--no-configs", action="store_true", help="(dev) skip the extra BASELINE configurations")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="(dev) images per chunk of the host pipeline")
     ap.add_argument("--workload", default="fundus", choices=sorted(WORKLOADS), help="(dev) default = BASELINE configs[1]")
     args = ap.parse_args()
-    select_workload(args.workload)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

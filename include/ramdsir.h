@@ -176,6 +176,37 @@ int ramdsir_mix_host_u8(ramdsir_pipe_t* pipe, const unsigned char* src_host, con
                         const int64_t* partner_idx_host, const int32_t* ratio_k_host, float* out_host,
                         int B, int n_bank, int ratio_den, float clip_lo, float clip_hi, float scale,
                         float shift);
+/*
+ * Device-side partner / ratio selection with host-identical MT19937 streams (what Fundus_Multi.__getitem__ draws per
+ * sample: np.random.choice(domain_list, 1)[0], np.random.choice(partner_list), random.randint(1, 10) --
+ * fundus.py:205,208,35, prostate.py:182-183 -- from the per-worker streams seeded by seed_worker, train.py:80-83).
+ * A handle owns one (numpy, python) MT19937 state pair per worker stream ON THE DEVICE, seeded exactly like
+ * np.random.seed(s) / random.seed(s).  Stream s draws partners among candidates[s][0 .. n_candidates[s]) (domain
+ * indices; the caller removes the test domain and, for is_out_domain, the stream's own domain) and, inside the chosen
+ * domain d, an image in [0, domain_sizes[d]).  ramdsir_rng_draw produces, for every stream, the next n_per_stream
+ * samples' selections: partner_idx_dev[s * n + i] = row of the concatenated bank (domain offset + image index), and
+ * ratio_k_dev[s * n + i] in [ratio_lo, ratio_hi] -- bit-identical to calling the reference's draws in a loop on the
+ * host, including the number of 32-bit outputs each rejection loop consumes.  `candidates` is [n_streams][8].
+ * ramdsir_rng_seed_host / ramdsir_rng_get_state expose the raw states in numpy's get_state() layout (624 words +
+ * position; ramdsir_rng_state_words() == 625) so the streams can be handed back and forth with the host generators.
+ */
+typedef struct ramdsir_rng ramdsir_rng_t;
+int ramdsir_rng_state_words(void);
+int ramdsir_rng_seed_host(uint32_t worker_seed, uint32_t* numpy_state, uint32_t* python_state);
+int ramdsir_rng_create(ramdsir_rng_t** rng, int n_streams, const uint32_t* worker_seeds, int n_domains,
+                       const int32_t* domain_sizes, const int32_t* n_candidates, const int32_t* candidates);
+void ramdsir_rng_destroy(ramdsir_rng_t* rng);
+int ramdsir_rng_draw(ramdsir_rng_t* rng, int n_per_stream, int64_t* partner_idx_dev, int32_t* ratio_k_dev, int ratio_lo,
+                     int ratio_hi, void* stream);
+int ramdsir_rng_get_state(ramdsir_rng_t* rng, int stream_index, uint32_t* numpy_state, uint32_t* python_state);
+
+/*
+ * Device-side fundus mask encoding (fundus.py:227-239 + to_multilabel, transform.py:10-14): 8-bit mask [B, H, W]
+ * (grey > 200 background, 51..200 disc rim, <= 50 cup) -> float32 multilabel [B, 2, H, W]: channel 0 = cup,
+ * channel 1 = disc (cup included).  Byte work: bit-exact.
+ */
+int ramdsir_encode_fundus_mask_u8(const uint8_t* mask_dev, float* out_dev, int B, int H, int W, void* stream);
+
 /* number of kernel launches the library has issued on this process so far (bench bookkeeping) */
 uint64_t ramdsir_launch_count(void);
 

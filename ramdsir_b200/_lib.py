@@ -12,9 +12,9 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libramdsir.so")
+LIB_PATH = os.environ.get("RAMDSIR_LIB") or os.path.join(_HERE, "libramdsir.so")   # RAMDSIR_LIB: dev builds of the same ABI
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["ramdsir_abi.cu", "ram_fused.cu", "ram_generic.cu", "ram_multipass.cu"]
+SOURCES = ["ramdsir_abi.cu", "ram_fused.cu", "ram_generic.cu", "ram_multipass.cu", "ram_select.cu"]
 
 FLAG_INDEPENDENT, FLAG_SERIAL, FLAG_PATH_GENERIC, FLAG_RUNTIME_SHAPE = 1, 2, 4, 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
@@ -28,6 +28,8 @@ SYMBOLS = [
     "ramdsir_u8_supported", "ramdsir_bank_build_u8", "ramdsir_mix_dual_u8",
     "ramdsir_amp_spectrum_workspace_bytes", "ramdsir_amp_spectrum_f32", "ramdsir_band_blend_f32",
     "ramdsir_pipe_create", "ramdsir_pipe_destroy", "ramdsir_mix_host_f32", "ramdsir_mix_host_u8", "ramdsir_launch_count",
+    "ramdsir_rng_state_words", "ramdsir_rng_seed_host", "ramdsir_rng_create", "ramdsir_rng_destroy", "ramdsir_rng_draw",
+    "ramdsir_rng_get_state", "ramdsir_encode_fundus_mask_u8",
 ]
 
 
@@ -91,6 +93,14 @@ def _declare(lib):
     lib.ramdsir_mix_host_f32.argtypes = [vp] * 6 + [c.c_int] * 3 + [c.c_float] * 4
     lib.ramdsir_mix_host_u8.argtypes = [vp] * 6 + [c.c_int] * 3 + [c.c_float] * 4
     lib.ramdsir_launch_count.restype = c.c_uint64
+    u32p = c.POINTER(c.c_uint32)
+    lib.ramdsir_rng_seed_host.argtypes = [c.c_uint32, vp, vp]
+    lib.ramdsir_rng_create.argtypes = [c.POINTER(vp), c.c_int, vp, c.c_int, vp, vp, vp]
+    lib.ramdsir_rng_destroy.argtypes = [vp]
+    lib.ramdsir_rng_destroy.restype = None
+    lib.ramdsir_rng_draw.argtypes = [vp, c.c_int, vp, vp, c.c_int, c.c_int, vp]
+    lib.ramdsir_rng_get_state.argtypes = [vp, c.c_int, vp, vp]
+    lib.ramdsir_encode_fundus_mask_u8.argtypes = [vp, vp, c.c_int, c.c_int, c.c_int, vp]
     return lib
 
 

@@ -88,8 +88,13 @@ ram_fused_kernel(const FusedShape S, const float* __restrict__ src, const float*
 // path) that signal an mbarrier: no thread holds patch values in registers across the column passes.
 __device__ __forceinline__ float4 ldg_policy(const float4* p, unsigned long long pol) {
   float4 v;
+#ifdef RD_EXP_NOALLOC
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+#else
   asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+#endif
   return v;
 }
 // uint8 sources (images straight from the decoder, fundus.py:205-214 hands RAM uint8-valued pixels): one 32-bit load
@@ -541,7 +546,11 @@ int launch_static(const FusedPlan& p, const StaticArgs& a, cudaStream_t st) {
     if (a.clean) fp.wr[fp.nwr++] = rng(a.clean, out_bytes);
     const bool pdl = trail_push(dev, st, fp, (a.flags & RAMDSIR_FLAG_INDEPENDENT) != 0) && !(a.flags & RAMDSIR_FLAG_SERIAL);
     EpiSat es;
+#ifdef RD_EXP_NOSAT
+    if (false) {
+#else
     if (epilogue_sat(a.ep, es, ms.dscale, ms.dc_add)) {
+#endif
       if (a.clean) return launch_static_one<CFG, false, true, TIn, EpiSat>(p, a, es, ms, pdl, st);
       return launch_static_one<CFG, false, false, TIn, EpiSat>(p, a, es, ms, pdl, st);
     }

@@ -107,12 +107,24 @@ RD_HD void f1_direct(const SH& S, unsigned char* sm, int strip, int half, int u)
     khi[mi] = (kh >= -S.b && kh <= S.b) ? kh + S.b : -1;
     acc[mi] = cf{0.f, 0.f};
   }
+  const float2 e0 = E2[((k2l * S.N1h) * 16 + c) * 2 + col];
+  bool alleq = true;
   for (int h1 = 0; h1 < S.N1h; ++h1) {
     const float2 e = E2[((k2l * S.N1h + h1) * 16 + c) * 2 + col];
     const cf ev{e.x, e.y};
+    alleq = alleq && e.x == e0.x && e.y == e0.y;
 #pragma unroll
     for (int mi = 0; mi <= 2 * MMAX; ++mi)
       if (khi[mi] >= 0) cmac(acc[mi], ev, ldcf(tw1 + 2 * (h1 * S.nb + khi[mi])));
+  }
+  // Degenerate columns.  For k2 == 0 the rows are kh = 16 k1 and the sum is an N1h-point DFT of the stride sums.  When
+  // those are all EQUAL (a constant column) it is exactly N1h e at k1 == 0 and exactly 0 elsewhere -- which is what a
+  // butterfly FFT (pocketfft behind the reference's np.fft.fft2, fundus.py:16,46) returns, whereas a direct sum of
+  // roots of unity leaves rounding noise whose phase the blend would then keep (np.angle(0) == 0, fundus.py:49).
+  if (k2 == 0 && alleq) {
+#pragma unroll
+    for (int mi = 0; mi <= 2 * MMAX; ++mi)
+      acc[mi] = (mi == MMAX) ? cf{e0.x * (float)S.N1h, e0.y * (float)S.N1h} : cf{0.f, 0.f};
   }
 #pragma unroll
   for (int mi = 0; mi <= 2 * MMAX; ++mi)
@@ -151,13 +163,30 @@ RD_HD cf band_spectrum(const SH& S, const unsigned char* sm, int kh, int kw) {
   const float4* zp = Z + (size_t)(kh + S.b) * S.pitchZ + S.N1w * (kw & 15);
   const float4* zm = Z + (size_t)(S.b - kh) * S.pitchZ + S.N1w * ((16 - (kw & 15)) & 15);
   cf upa{0, 0}, upb{0, 0}, uma{0, 0}, umb{0, 0};
+  const float4 p0 = zp[0], q0 = zm[0];
+  bool peq = true, qeq = true;
   for (int c1 = 0; c1 < S.N1w; ++c1) {
     const cf w = ldcf(tw2 + 2 * c1 * (S.b + 1));  // W_M^(c1 kw)
     const float4 p = zp[c1], q = zm[c1];
+    peq = peq && p.x == p0.x && p.y == p0.y && p.z == p0.z && p.w == p0.w;
+    qeq = qeq && q.x == q0.x && q.y == q0.y && q.z == q0.z && q.w == q0.w;
     cmac(upa, cf{p.x, p.y}, w);
     cmac(upb, cf{p.z, p.w}, w);
     cmacc(uma, cf{q.x, q.y}, w);  // U[-kh][-kw] uses W_M^(-c1 kw)
     cmacc(umb, cf{q.z, q.w}, w);
+  }
+  // Degenerate rows (see f1_direct): for kw = 16 q the sum over c1 is an N1w-point DFT; equal terms give exactly
+  // N1w z at q == 0 and exactly 0 elsewhere, as the butterflies of the reference's FFT do.
+  if ((kw & 15) == 0) {
+    const float n = (float)S.N1w;
+    if (peq) {
+      upa = (kw == 0) ? cf{p0.x * n, p0.y * n} : cf{0.f, 0.f};
+      upb = (kw == 0) ? cf{p0.z * n, p0.w * n} : cf{0.f, 0.f};
+    }
+    if (qeq) {
+      uma = (kw == 0) ? cf{q0.x * n, q0.y * n} : cf{0.f, 0.f};
+      umb = (kw == 0) ? cf{q0.z * n, q0.w * n} : cf{0.f, 0.f};
+    }
   }
   // G0 = (Ua+ + conj(Ua-))/2, G2 = (Ua+ - conj(Ua-))/(2i); G1, G3 likewise from Ub
   const cf g0{0.5f * (upa.re + uma.re), 0.5f * (upa.im - uma.im)};

@@ -35,15 +35,25 @@ __global__ void g_row_fwd(GShape S, int nkw, const float* __restrict__ src, cons
     row[w] = x[w];
   }
   __syncthreads();
+  // Degenerate rows.  A constant row transforms to exactly W c at kw == 0 and exactly 0 elsewhere under a butterfly
+  // FFT (pocketfft behind the reference's np.fft.fft2, fundus.py:16,46); a direct sum of roots of unity leaves rounding
+  // noise instead, whose phase the blend would then keep (np.angle(0) == 0, fundus.py:49).  Detect it exactly.
+  bool eq = true;
+  for (int w = threadIdx.x; w < S.W; w += blockDim.x) eq = eq && row[w] == row[0];
+  const bool constant = __syncthreads_and(eq);
   for (int kw = threadIdx.x; kw < nkw; kw += blockDim.x) {
     float re = 0.f, im = 0.f;
-    int idx = 0;
-    for (int w = 0; w < S.W; ++w) {
-      const float2 t = tw[idx];
-      re = fmaf(row[w], t.x, re);
-      im = fmaf(row[w], t.y, im);
-      idx += kw;
-      if (idx >= S.W) idx -= S.W;
+    if (constant) {
+      re = (kw == 0) ? row[0] * (float)S.W : 0.f;
+    } else {
+      int idx = 0;
+      for (int w = 0; w < S.W; ++w) {
+        const float2 t = tw[idx];
+        re = fmaf(row[w], t.x, re);
+        im = fmaf(row[w], t.y, im);
+        idx += kw;
+        if (idx >= S.W) idx -= S.W;
+      }
     }
     T[(plane * S.H + h) * (size_t)nkw + kw] = make_float2(re, im);
   }
@@ -62,18 +72,25 @@ __global__ void g_col_full_amp(GShape S, int nkw, const float2* __restrict__ T, 
     col[h] = T[(plane * S.H + h) * (size_t)nkw + kw];
   }
   __syncthreads();
+  bool eq = true;                       // degenerate columns, as in g_row_fwd
+  for (int h = threadIdx.x; h < S.H; h += blockDim.x) eq = eq && col[h].x == col[0].x && col[h].y == col[0].y;
+  const bool constant = __syncthreads_and(eq);
   float* a = amp + plane * (size_t)S.H * S.W;
   for (int kh = threadIdx.x; kh < S.H; kh += blockDim.x) {
     float re = 0.f, im = 0.f;
-    int idx = 0;
-    for (int h = 0; h < S.H; ++h) {
-      const float2 t = tw[idx], v = col[h];
-      re = fmaf(v.x, t.x, re);
-      re = fmaf(-v.y, t.y, re);
-      im = fmaf(v.x, t.y, im);
-      im = fmaf(v.y, t.x, im);
-      idx += kh;
-      if (idx >= S.H) idx -= S.H;
+    if (constant) {
+      if (kh == 0) { re = col[0].x * (float)S.H; im = col[0].y * (float)S.H; }
+    } else {
+      int idx = 0;
+      for (int h = 0; h < S.H; ++h) {
+        const float2 t = tw[idx], v = col[h];
+        re = fmaf(v.x, t.x, re);
+        re = fmaf(-v.y, t.y, re);
+        im = fmaf(v.x, t.y, im);
+        im = fmaf(v.y, t.x, im);
+        idx += kh;
+        if (idx >= S.H) idx -= S.H;
+      }
     }
     const float m = sqrtf(re * re + im * im);
     a[(size_t)kh * S.W + kw] = m;
@@ -112,20 +129,27 @@ __global__ void g_col_fwd_band(GShape S, const float2* __restrict__ T, const flo
     col[h] = T[(plane * S.H + h) * (size_t)(S.b + 1) + kw];
   }
   __syncthreads();
+  bool eq = true;                       // degenerate columns, as in g_row_fwd
+  for (int h = threadIdx.x; h < S.H; h += blockDim.x) eq = eq && col[h].x == col[0].x && col[h].y == col[0].y;
+  const bool constant = __syncthreads_and(eq);
   const size_t patch_px = (size_t)S.nb * S.nb;
   for (int khi = threadIdx.x; khi < S.nb; khi += blockDim.x) {
     const int kh = khi - S.b;
     const int step = ((kh % S.H) + S.H) % S.H;
     float re = 0.f, im = 0.f;
-    int idx = 0;
-    for (int h = 0; h < S.H; ++h) {
-      const float2 t = tw[idx], v = col[h];
-      re = fmaf(v.x, t.x, re);
-      re = fmaf(-v.y, t.y, re);
-      im = fmaf(v.x, t.y, im);
-      im = fmaf(v.y, t.x, im);
-      idx += step;
-      if (idx >= S.H) idx -= S.H;
+    if (constant) {
+      if (kh == 0) { re = col[0].x * (float)S.H; im = col[0].y * (float)S.H; }
+    } else {
+      int idx = 0;
+      for (int h = 0; h < S.H; ++h) {
+        const float2 t = tw[idx], v = col[h];
+        re = fmaf(v.x, t.x, re);
+        re = fmaf(-v.y, t.y, re);
+        im = fmaf(v.x, t.y, im);
+        im = fmaf(v.y, t.x, im);
+        idx += step;
+        if (idx >= S.H) idx -= S.H;
+      }
     }
     const float a2 = re * re + im * im;
     if (BANK) {

@@ -28,7 +28,7 @@ from torch.utils.data import Dataset
 
 from .api import FUNDUS_EPILOGUE, PROSTATE_EPILOGUE, build_amp_bank, ram_mix_batch
 
-__all__ = ["Fundus_Multi", "Prostate_Multi", "RamBatchHook", "encode_fundus_mask"]
+__all__ = ["Fundus_Multi", "Prostate_Multi", "RamBatchHook", "encode_fundus_mask", "encode_fundus_mask_batch"]
 
 
 def encode_fundus_mask(mask_img) -> torch.Tensor:
@@ -42,6 +42,21 @@ def encode_fundus_mask(mask_img) -> torch.Tensor:
     out[0] = m <= 50
     out[1] = m <= 200
     return torch.from_numpy(out)
+
+
+def encode_fundus_mask_batch(mask_u8: torch.Tensor, stream=None) -> torch.Tensor:
+    """Device-side mask encoding (ramdsir_encode_fundus_mask_u8): uint8 CUDA [B, H, W] -> float32 [B, 2, H, W], the
+    same two comparisons as `encode_fundus_mask` (fundus.py:227-239 + transform.py:10-14), bit-exact."""
+    from . import _lib
+    if not (isinstance(mask_u8, torch.Tensor) and mask_u8.is_cuda and mask_u8.dtype == torch.uint8 and mask_u8.dim() == 3):
+        raise TypeError("mask_u8 must be a CUDA uint8 tensor [B, H, W]")
+    mask_u8 = mask_u8.contiguous()
+    bsz, h, w = mask_u8.shape
+    out = torch.empty((bsz, 2, h, w), dtype=torch.float32, device=mask_u8.device)
+    with torch.cuda.device(mask_u8.device):
+        s = torch.cuda.current_stream() if stream is None else stream
+        _lib.check(_lib.load().ramdsir_encode_fundus_mask_u8(mask_u8.data_ptr(), out.data_ptr(), bsz, h, w, int(s.cuda_stream)))
+    return out
 
 
 def _gpu_ram_one(src_chw_f32: np.ndarray, partner_chw_f32: np.ndarray, ratio_k: int, epilogue, L=0.1) -> torch.Tensor:

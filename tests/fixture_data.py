@@ -24,9 +24,10 @@ def _blobs(rs, h, w, c):
     return y
 
 
-def make_fundus(root):
+def make_fundus(root, counts=None):
+    """`counts` (domain -> images) defaults to FUNDUS_DOMAINS, the fixture the dataset goldens were recorded on."""
     rs = np.random.RandomState(20221017)
-    for dom, n in FUNDUS_DOMAINS.items():
+    for dom, n in (FUNDUS_DOMAINS if counts is None else counts).items():
         os.makedirs(os.path.join(root, dom, "train", "ROIs", "image"), exist_ok=True)
         os.makedirs(os.path.join(root, dom, "train", "ROIs", "mask"), exist_ok=True)
         top, inner = [], []

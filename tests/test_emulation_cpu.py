@@ -50,8 +50,9 @@ def _ptr(a, t=ctypes.POINTER(ctypes.c_float)):
 
 
 CASES = [  # (entry point, C, H, W, integer-valued, constant plane?, bank tolerance)
-    ("emul_fused", 2, 64, 128, True, False),            # runtime-shape kernel (direct sums)
+    ("emul_fused", 2, 64, 128, True, True),             # runtime-shape kernel (direct sums + exact degenerate rule)
     ("emul_fused", 1, 256, 256, True, False),
+    ("emul_fused", 2, 128, 192, False, True),
     ("emul_fused_static", 2, 256, 256, True, True),     # default kernels, incl. a constant plane
     ("emul_fused_static", 1, 384, 384, False, True),
     ("emul_multipass", 1, 512, 512, True, False),       # K2

@@ -166,11 +166,16 @@ def test_white_noise_inputs(R):
     check(got, want, "white noise")
 
 
-@pytest.mark.parametrize("shape", [(3, 256, 256, True), (1, 384, 384, False)])
+@pytest.mark.parametrize("shape", [(3, 256, 256, True, None), (1, 384, 384, False, None), (2, 64, 128, True, None),
+                                   (2, 128, 192, False, None), (3, 256, 256, True, "runtime"), (2, 33, 45, True, None),
+                                   (1, 50, 64, False, None), (3, 256, 256, True, "generic")],
+                         ids=["static256", "static384", "runtime64x128", "runtime128x192", "runtime256", "generic33x45",
+                              "generic50x64", "generic256"])
 def test_constant_planes_take_phase_zero_like_the_reference(R, shape):
     """A constant plane has EXACT zeros off DC in the reference's butterfly FFT, so those bins take
-    phase 0 (np.angle(0) == 0).  The static fused kernels keep every stage a butterfly and match."""
-    c, h, w, integer = shape
+    phase 0 (np.angle(0) == 0).  The static fused kernels keep every stage a butterfly; the runtime-shape and the
+    generic kernels detect constant rows / columns exactly and return the butterfly result.  Every path matches."""
+    c, h, w, integer, path = shape
     rs = np.random.RandomState(17)
     lo, hi = (0, 255) if integer else (-1, 1)
     src = _smooth(rs, (3, c, h, w), lo, hi, integer)
@@ -179,8 +184,17 @@ def test_constant_planes_take_phase_zero_like_the_reference(R, shape):
     src[1] = 0.0                                    # an all-zero image
     pidx, rk = np.array([0, 1, 1]), np.array([3, 7, 5], np.int32)
     epi = O.FUNDUS_EPILOGUE if integer else O.PROSTATE_EPILOGUE
-    got, _ = gpu_mix(R, src, par, pidx, rk, 0.1, epi)
+    got, bank = gpu_mix(R, src, par, pidx, rk, 0.1, epi, path=path)
     check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "constant planes")
+    # the bank of degenerate planes: exact zeros off DC, like extract_amp_spectrum
+    flat = np.stack([src[0], src[1]])
+    _, bank_flat = gpu_mix(R, src[:1], flat, [0], [5], 0.1, epi, path=path)
+    want_bank = O.build_bank(flat, 0.1)
+    b = want_bank.shape[-1] // 2
+    assert bank_flat[0, 0, b, b] == pytest.approx(want_bank[0, 0, b, b], rel=1e-6)
+    off = np.ones_like(bank_flat[0, 0], bool)
+    off[b, b] = False
+    assert (bank_flat[0, 0][off] == 0).all() and (bank_flat[1] == 0).all()
 
 
 @pytest.mark.parametrize("shape", [(3, 256, 256, True), (1, 384, 384, False)], ids=["fundus", "prostate"])
@@ -369,10 +383,9 @@ def test_multipass_oracle_parity(R, shape):
     got, bank = gpu_mix(R, src, par, pidx, rk, 0.1, epi)
     check(got, O.mix_batch(src, par, pidx, rk, 0.1, epi=epi), "multipass %s" % (shape,))
     assert O.rel_l2(bank, O.build_bank(par, 0.1)) <= 1e-6
-    # cross-check against the independent generic kernels (they use direct sums, so the degenerate
-    # constant-plane image is left out: see DESIGN.md "Conditioning note")
-    g, _ = gpu_mix(R, src[:2], par, pidx[:2], rk[:2], 0.1, epi, force_generic=True)
-    check(got[:2], g, "multipass vs generic")
+    # cross-check against the independent generic kernels, constant plane included
+    g, _ = gpu_mix(R, src, par, pidx, rk, 0.1, epi, force_generic=True)
+    check(got, g, "multipass vs generic")
 
 
 def test_hires_1024(R):
