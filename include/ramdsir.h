@@ -207,6 +207,28 @@ int ramdsir_rng_get_state(ramdsir_rng_t* rng, int stream_index, uint32_t* numpy_
  */
 int ramdsir_encode_fundus_mask_u8(const uint8_t* mask_dev, float* out_dev, int B, int H, int W, void* stream);
 
+/*
+ * GPU versions of the loader's geometric transforms on 8-bit images, bit-exact with Pillow (which the reference calls):
+ *   ramdsir_resize_u8        <- img.resize(size, BILINEAR) / mask.resize(size, NEAREST)   dataset/transform.py:163-177,
+ *                               193-196; partner resize dataset/fundus.py:209
+ *   ramdsir_crop_pad_chw_u8  <- RandomCrop's right/bottom padding + crop                  dataset/transform.py:25-38
+ *                               (+ the HWC -> CHW transpose the RAM block does next,      dataset/fundus.py:211-212)
+ * Images are interleaved HWC uint8 on the device, as np.array(PIL image) lays them out.  `filter` uses Pillow's numbering.
+ * Bilinear is Pillow's two-pass fixed-point convolution (horizontal first, 8-bit intermediate, 22-bit coefficients),
+ * nearest its running-sum index table; the tables are built on the host exactly as Pillow builds them
+ * (ramdsir_resize_tables_host exposes them: bilinear -> bounds [out][2] = (first, count), kk [out][ksize];
+ * nearest -> bounds [out] = source index).  x0 / y0 of the crop may be negative or run past the image: pixels outside
+ * are `fill` (the reference pads images with 0 and masks with 255).
+ */
+#define RAMDSIR_FILTER_NEAREST 0
+#define RAMDSIR_FILTER_BILINEAR 2
+size_t ramdsir_resize_workspace_bytes(int Hin, int Win, int C, int Hout, int Wout);
+int ramdsir_resize_u8(const uint8_t* src_dev, int Hin, int Win, int C, uint8_t* dst_dev, int Hout, int Wout, int filter,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+int ramdsir_crop_pad_chw_u8(const uint8_t* src_hwc_dev, int H, int W, int C, int x0, int y0, int out_h, int out_w,
+                            int fill, uint8_t* dst_chw_dev, void* stream);
+int ramdsir_resize_tables_host(int in_size, int out_size, int filter, int32_t* bounds, int32_t* kk, int* ksize);
+
 /* number of kernel launches the library has issued on this process so far (bench bookkeeping) */
 uint64_t ramdsir_launch_count(void);
 

@@ -14,8 +14,9 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RAMDSIR_LIB") or os.path.join(_HERE, "libramdsir.so")   # RAMDSIR_LIB: dev builds of the same ABI
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["ramdsir_abi.cu", "ram_fused.cu", "ram_generic.cu", "ram_multipass.cu", "ram_select.cu"]
+SOURCES = ["ramdsir_abi.cu", "ram_fused.cu", "ram_generic.cu", "ram_multipass.cu", "ram_select.cu", "ram_transform.cu"]
 
+FILTER_NEAREST, FILTER_BILINEAR = 0, 2
 FLAG_INDEPENDENT, FLAG_SERIAL, FLAG_PATH_GENERIC, FLAG_RUNTIME_SHAPE = 1, 2, 4, 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
 PATH_NONE, PATH_FUSED, PATH_MULTIPASS, PATH_GENERIC = 0, 1, 2, 3
@@ -30,6 +31,7 @@ SYMBOLS = [
     "ramdsir_pipe_create", "ramdsir_pipe_destroy", "ramdsir_mix_host_f32", "ramdsir_mix_host_u8", "ramdsir_launch_count",
     "ramdsir_rng_state_words", "ramdsir_rng_seed_host", "ramdsir_rng_create", "ramdsir_rng_destroy", "ramdsir_rng_draw",
     "ramdsir_rng_get_state", "ramdsir_encode_fundus_mask_u8",
+    "ramdsir_resize_workspace_bytes", "ramdsir_resize_u8", "ramdsir_crop_pad_chw_u8", "ramdsir_resize_tables_host",
 ]
 
 
@@ -101,6 +103,11 @@ def _declare(lib):
     lib.ramdsir_rng_draw.argtypes = [vp, c.c_int, vp, vp, c.c_int, c.c_int, vp]
     lib.ramdsir_rng_get_state.argtypes = [vp, c.c_int, vp, vp]
     lib.ramdsir_encode_fundus_mask_u8.argtypes = [vp, vp, c.c_int, c.c_int, c.c_int, vp]
+    lib.ramdsir_resize_workspace_bytes.argtypes = [c.c_int] * 5
+    lib.ramdsir_resize_workspace_bytes.restype = c.c_size_t
+    lib.ramdsir_resize_u8.argtypes = [vp, c.c_int, c.c_int, c.c_int, vp, c.c_int, c.c_int, c.c_int, vp, c.c_size_t, vp]
+    lib.ramdsir_crop_pad_chw_u8.argtypes = [vp] + [c.c_int] * 8 + [vp, vp]
+    lib.ramdsir_resize_tables_host.argtypes = [c.c_int, c.c_int, c.c_int, vp, vp, c.POINTER(c.c_int)]
     return lib
 
 

@@ -1,14 +1,11 @@
 // Multi-pass RAM kernels (K2) for sm_100a: 512^2 (b = 51) and 1024^2 (b = 102).  See ram_multipass.cuh.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
 #include <vector>
 #include "ram_internal.h"
 #include "ram_multipass_host.h"
-
-#ifndef RAMDSIR_MP_CHUNK_MB
-#define RAMDSIR_MP_CHUNK_MB 1024   // planes per pass = this budget / (x + band workspace per plane). Measured on B200 (64x3x1024^2): 9-plane chunks 42k img/s, 18: 64.6k, 36: 66.9k -- L2 does not retain 4 MB planes between passes, so fewer, larger launches win
-#endif
 
 namespace ramdsir {
 
@@ -23,21 +20,15 @@ __device__ __forceinline__ void mp_stg_policy(float4* p, float4 v, unsigned long
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
 }
 
-// ---- pass A: forward columns of one (plane, strip) -> Zg[plane][kh][strip columns] --------------------
+// ===== task bodies (one CTA each).  `zg` is the plane's band rows in the workspace: [nb][M] float4, read with
+// ld.global.cg (they are produced by other CTAs and have no reuse in L1). ============================================
+
+// ---- A: forward columns of one (plane, strip) -> zg[kh][strip columns] ------------------------------------------
 template <class CFG>
-__global__ void __launch_bounds__(256, 2)
-ram_mp_pass_a(const float* __restrict__ src, float4* __restrict__ Zg, const float* __restrict__ tables, int plane0) {
-  extern __shared__ __align__(16) unsigned char sm[];
-  const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, lp = blockIdx.x / CFG::nstrips;
-  unsigned long long pol_keep;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-  {
-    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
-    const float4* g = reinterpret_cast<const float4*>(tables);
-    for (int i = tid; i < CFG::tabBytes / 16; i += 256) tab[i] = g[i];
-  }
-  __syncthreads();
-  const float4* x4 = reinterpret_cast<const float4*>(src + (size_t)(plane0 + lp) * CFG::H * CFG::W);
+__device__ __forceinline__ void mp_task_a(unsigned char* sm, const float* __restrict__ src, float4* __restrict__ zgp,
+                                          int plane, int strip, unsigned long long pol_keep) {
+  const int tid = threadIdx.x;
+  const float4* x4 = reinterpret_cast<const float4*>(src + (size_t)plane * CFG::H * CFG::W);
   auto ld = [&](size_t off) { return mp_ldg_policy(x4 + off, pol_keep); };
   for (int p = 0; p < CFG::HP; ++p) {
     cf va[16], vb[16];
@@ -51,41 +42,33 @@ ram_mp_pass_a(const float* __restrict__ src, float4* __restrict__ Zg, const floa
     }
   }
   const float4* Zs = reinterpret_cast<const float4*>(sm + CFG::offZ);
-  float4* zg = Zg + (size_t)lp * CFG::nb * CFG::M + strip * 16;
+  float4* zg = zgp + strip * 16;
   for (int i = tid; i < CFG::nb * 16; i += 256) zg[(size_t)(i >> 4) * CFG::M + (i & 15)] = Zs[(i >> 4) * CFG::pitchZ + (i & 15)];
 }
 
-// ---- pass B: KG pairs of rows (+kh, -kh) of one plane: row FFTs, band update, inverse row FFTs, in place ----
-template <class CFG, bool BANK>
-__global__ void __launch_bounds__(CFG::bThreads)
-ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank, const int64_t* __restrict__ pidx,
-              const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ bank_out,
-              const float* __restrict__ tables, int plane0) {
-  extern __shared__ __align__(16) unsigned char sm[];
-  constexpr int NT = CFG::bThreads, KG = CFG::KG, M = CFG::M, RP = 2 * CFG::rowPitch, DP = 2 * (CFG::b + 1);
-  const int tid = threadIdx.x, kh0 = (blockIdx.x % CFG::nkg) * KG, lp = blockIdx.x / CFG::nkg;
-  const int plane = plane0 + lp;
+// ---- B: KG pairs of rows (+kh, -kh) of one plane: row FFTs, band update, inverse row FFTs, in place on zg ----------
+// `sm` is the CTA's work area (R, D, P at CFG::bOff*), `tab` the pass-B tables wherever the caller keeps them.
+template <class CFG, bool BANK, int NT>
+__device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, float4* __restrict__ zplane,
+                                          const float* __restrict__ bank, const int64_t* __restrict__ pidx,
+                                          const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C,
+                                          float* __restrict__ bank_out, int plane, int gplane, int kg) {
+  constexpr int KG = CFG::KG, M = CFG::M, RP = 2 * CFG::rowPitch, DP = 2 * (CFG::b + 1);
+  const int tid = threadIdx.x, kh0 = kg * KG;
   const int ng = (CFG::b + 1 - kh0 < KG) ? CFG::b + 1 - kh0 : KG;     // kh values handled here
-  {
-    float4* tab4 = reinterpret_cast<float4*>(sm + CFG::bOffTab);
-    const float4* g = reinterpret_cast<const float4*>(tables);
-    for (int i = tid; i < CFG::bTabBytes / 16; i += NT) tab4[i] = g[i];
-  }
   float4* R = reinterpret_cast<float4*>(sm + CFG::bOffR);
   float2* D = reinterpret_cast<float2*>(sm + CFG::bOffD);
-  const float* tab = reinterpret_cast<const float*>(sm + CFG::bOffTab);
-  float4* zplane = Zg + (size_t)lp * CFG::nb * M;
   // row slot r = 2 g + s  <->  band row  b + kh (s = 0)  /  b - kh (s = 1),  kh = kh0 + g  (kh = 0 uses s = 0 only)
   auto zrow = [&](int r) { const int kh = kh0 + (r >> 1); return zplane + (size_t)(CFG::b + ((r & 1) ? -kh : kh)) * M; };
   auto live = [&](int r) { return !((r & 1) && kh0 + (r >> 1) == 0); };
   for (int i = tid; i < ng * 2 * M; i += NT) {
     const int r = i / M, m = i % M;
-    if (live(r)) R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)] = zrow(r)[m];
+    if (live(r)) R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)] = __ldcg(zrow(r) + m);
   }
   // stage the partner-patch rows b + kh and b - kh of every kh handled here (coalesced; consumed by the band tasks)
   float omr = 0.f;
   if (!BANK) {
-    const int img = plane / C, ch = plane - img * C;
+    const int img = gplane / C, ch = gplane - img * C;
     const long long p = pidx[img];
     const bool ok = (p >= 0 && p < (long long)n_bank);
     omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
@@ -115,59 +98,52 @@ ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank, const int
       const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
       if (live(2 * g + srow)) m_band<CFG, true>(R + (size_t)g * RP, D + g * DP, tab, nullptr, patch, 0.f, kh0 + g, srow, tt % (CFG::b + 1));
     }
-    return;
-  }
-  {
-    const float* P = reinterpret_cast<const float*>(sm + CFG::bOffP);
-    for (int t = tid; t < ng * nband; t += NT) {
-      const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
-      if (live(2 * g + srow)) m_band<CFG, false>(R + (size_t)g * RP, D + g * DP, tab, P + g * 2 * CFG::nb, nullptr, omr, kh0 + g, srow, tt % (CFG::b + 1));
+  } else {
+    {
+      const float* P = reinterpret_cast<const float*>(sm + CFG::bOffP);
+      for (int t = tid; t < ng * nband; t += NT) {
+        const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
+        if (live(2 * g + srow)) m_band<CFG, false>(R + (size_t)g * RP, D + g * DP, tab, P + g * 2 * CFG::nb, nullptr, omr, kh0 + g, srow, tt % (CFG::b + 1));
+      }
     }
-  }
-  __syncthreads();
-  for (int i = tid; i < ng * RP; i += NT) R[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // everything off the band is zero
-  __syncthreads();
-  for (int t = tid; t < ng * 2 * CFG::nb; t += NT) {
-    const int g = t / (2 * CFG::nb), tt = t % (2 * CFG::nb), srow = tt / CFG::nb;
-    if (live(2 * g + srow)) m_put_v<CFG>(R + (size_t)g * RP, D + g * DP, tab, kh0 + g, srow, tt % CFG::nb);
-  }
-  __syncthreads();
-  for (int t = tid; t < ng * 32; t += NT) {
-    const int g = t / 32, tt = t % 32;
-    if (live(2 * g + tt / 16)) m_row_stage2<CFG, 1>(R + (size_t)g * RP, tt);
-  }
-  __syncthreads();
-  for (int t = tid; t < ng * 2 * CFG::N1w; t += NT) {
-    const int g = t / (2 * CFG::N1w), tt = t % (2 * CFG::N1w);
-    if (live(2 * g + tt / CFG::N1w)) m_row_stage1<CFG, 1>(R + (size_t)g * RP, tab, tt);
-  }
-  __syncthreads();
-  for (int i = tid; i < ng * 2 * M; i += NT) {
-    const int r = i / M, m = i % M;
-    if (live(r)) zrow(r)[m] = R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)];
+    __syncthreads();
+    for (int i = tid; i < ng * RP; i += NT) R[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // everything off the band is zero
+    __syncthreads();
+    for (int t = tid; t < ng * 2 * CFG::nb; t += NT) {
+      const int g = t / (2 * CFG::nb), tt = t % (2 * CFG::nb), srow = tt / CFG::nb;
+      if (live(2 * g + srow)) m_put_v<CFG>(R + (size_t)g * RP, D + g * DP, tab, kh0 + g, srow, tt % CFG::nb);
+    }
+    __syncthreads();
+    for (int t = tid; t < ng * 32; t += NT) {
+      const int g = t / 32, tt = t % 32;
+      if (live(2 * g + tt / 16)) m_row_stage2<CFG, 1>(R + (size_t)g * RP, tt);
+    }
+    __syncthreads();
+    for (int t = tid; t < ng * 2 * CFG::N1w; t += NT) {
+      const int g = t / (2 * CFG::N1w), tt = t % (2 * CFG::N1w);
+      if (live(2 * g + tt / CFG::N1w)) m_row_stage1<CFG, 1>(R + (size_t)g * RP, tab, tt);
+    }
+    __syncthreads();
+    for (int i = tid; i < ng * 2 * M; i += NT) {
+      const int r = i / M, m = i % M;
+      if (live(r)) zrow(r)[m] = R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)];
+    }
   }
 }
 
-// ---- pass C: inverse columns of one (plane, strip), + x, epilogue -------------------------------------
+// ---- C: inverse columns of one (plane, strip), + x, epilogue ---------------------------------------------------
 template <class CFG>
-__global__ void __launch_bounds__(256, 2)
-ram_mp_pass_c(const float* __restrict__ src, const float4* __restrict__ Zg, const int64_t* __restrict__ pidx, int n_bank,
-              int C, float* __restrict__ out, Epilogue ep, const float* __restrict__ tables, int plane0) {
-  extern __shared__ __align__(16) unsigned char sm[];
-  const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, lp = blockIdx.x / CFG::nstrips;
-  const int plane = plane0 + lp;
-  unsigned long long pol_stream;
-  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+__device__ __forceinline__ void mp_task_c(unsigned char* sm, const float* __restrict__ src, const float4* __restrict__ zgp,
+                                          const int64_t* __restrict__ pidx, int n_bank, int C, float* __restrict__ out,
+                                          Epilogue ep, int plane, int gplane, int strip, unsigned long long pol_stream) {
+  const int tid = threadIdx.x;
   {
-    float4* tab = reinterpret_cast<float4*>(sm + CFG::offTab);
-    const float4* g = reinterpret_cast<const float4*>(tables);
-    for (int i = tid; i < CFG::tabBytes / 16; i += 256) tab[i] = g[i];
     float4* Zs = reinterpret_cast<float4*>(sm + CFG::offZ);
-    const float4* zg = Zg + (size_t)lp * CFG::nb * CFG::M + strip * 16;
-    for (int i = tid; i < CFG::nb * 16; i += 256) Zs[(i >> 4) * CFG::pitchZ + (i & 15)] = zg[(size_t)(i >> 4) * CFG::M + (i & 15)];
+    const float4* zg = zgp + strip * 16;
+    for (int i = tid; i < CFG::nb * 16; i += 256) Zs[(i >> 4) * CFG::pitchZ + (i & 15)] = __ldcg(zg + (size_t)(i >> 4) * CFG::M + (i & 15));
   }
   {
-    const long long p = pidx[plane / C];
+    const long long p = pidx[gplane / C];
     if (p < 0 || p >= (long long)n_bank) ep.scale = __int_as_float(0x7fc00000);
   }
   __syncthreads();
@@ -191,6 +167,45 @@ ram_mp_pass_c(const float* __restrict__ src, const float4* __restrict__ Zg, cons
   }
 }
 
+// ===== the three passes as separate launches over all planes (same task bodies) ====================================
+template <class CFG>
+__global__ void __launch_bounds__(256, 2) ram_mp_pass_a(const float* __restrict__ src, float4* __restrict__ Zg, const float* __restrict__ tab_ac) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, plane = blockIdx.x / CFG::nstrips;
+  float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
+  for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
+  unsigned long long pol_keep;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  __syncthreads();
+  mp_task_a<CFG>(sm, src, Zg + (size_t)plane * CFG::nb * CFG::M, plane, strip, pol_keep);
+}
+template <class CFG, bool BANK>
+__global__ void __launch_bounds__(CFG::bThreads) ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank,
+    const int64_t* __restrict__ pidx, const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ bank_out,
+    const float* __restrict__ tab_b, int plane0) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int tid = threadIdx.x, kg = blockIdx.x % CFG::nkg, plane = blockIdx.x / CFG::nkg;
+  float4* t = reinterpret_cast<float4*>(sm + CFG::bOffTab);
+  for (int i = tid; i < CFG::bTabBytes / 16; i += CFG::bThreads) t[i] = reinterpret_cast<const float4*>(tab_b)[i];
+  __syncthreads();
+  // `plane` indexes this chunk's workspace and (bank mode) output; plane0 + plane is the batch-global plane whose
+  // image selects the partner and the ratio
+  mp_task_b<CFG, BANK, CFG::bThreads>(sm, reinterpret_cast<const float*>(sm + CFG::bOffTab), Zg + (size_t)plane * CFG::nb * CFG::M,
+                                      bank, pidx, rk, ratio_den, n_bank, C, bank_out, plane, plane0 + plane, kg);
+}
+template <class CFG>
+__global__ void __launch_bounds__(256, 2) ram_mp_pass_c(const float* __restrict__ src, const float4* __restrict__ Zg,
+    const int64_t* __restrict__ pidx, int n_bank, int C, float* __restrict__ out, Epilogue ep, const float* __restrict__ tab_ac, int plane0) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, plane = blockIdx.x / CFG::nstrips;
+  float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
+  for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
+  unsigned long long pol_stream;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  __syncthreads();
+  mp_task_c<CFG>(sm, src, Zg + (size_t)plane * CFG::nb * CFG::M, pidx, n_bank, C, out, ep, plane, plane0 + plane, strip, pol_stream);
+}
+
 // ---------------------------------------------------------------------------------------------
 namespace {
 using K512 = KCfg<512, 512, 51>;
@@ -199,10 +214,10 @@ using K1024 = KCfg<1024, 1024, 102>;
 struct MpPlan {
   float* tab_ac = nullptr;
   float* tab_b = nullptr;
-  int chunk = 1;
 };
 std::mutex g_mu;
 std::map<std::tuple<int, int>, MpPlan> g_plans;  // (device, H)
+std::map<int, cudaStream_t> g_upload;
 
 template <class CFG>
 int get_plan(MpPlan** out) {
@@ -216,33 +231,31 @@ int get_plan(MpPlan** out) {
     std::vector<float> a(CFG::tabBytes / 4), b(CFG::bTabBytes / 4);
     multipass_tables_ac<CFG>(a.data());
     multipass_tables_b<CFG>(b.data());
+    cudaStream_t& up = g_upload[dev];
+    if (!up) RD_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
     RD_CUDA(cudaMalloc(&p.tab_ac, CFG::tabBytes));
     RD_CUDA(cudaMalloc(&p.tab_b, CFG::bTabBytes));
-    RD_CUDA(cudaMemcpy(p.tab_ac, a.data(), CFG::tabBytes, cudaMemcpyHostToDevice));
-    RD_CUDA(cudaMemcpy(p.tab_b, b.data(), CFG::bTabBytes, cudaMemcpyHostToDevice));
-    RD_CUDA(cudaDeviceSynchronize());
+    RD_CUDA(cudaMemcpyAsync(p.tab_ac, a.data(), CFG::tabBytes, cudaMemcpyHostToDevice, up));
+    RD_CUDA(cudaMemcpyAsync(p.tab_b, b.data(), CFG::bTabBytes, cudaMemcpyHostToDevice, up));
+    RD_CUDA(cudaStreamSynchronize(up));      // a private stream: nobody else's work is synchronised
     RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_a<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
     RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_c<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
     RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_b<CFG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::bSmemBytes));
     RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_b<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::bSmemBytes));
-    // chunk of planes per pass: keep x (H*W*4 per plane) + Zg of a chunk well inside the 126 MB L2,
-    // and make planes*strips a multiple of the 296 resident CTAs where possible
-    int sms = 148;
-    RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t per_plane = (size_t)CFG::H * CFG::W * 4 + (size_t)CFG::nb * CFG::M * 16;
-    int chunk = (int)((size_t)RAMDSIR_MP_CHUNK_MB * 1024 * 1024 / per_plane);
-    const int wave = 2 * sms / CFG::nstrips;                 // planes per full wave (2 CTAs per SM) of pass A / C
-    if (chunk >= wave && wave > 0) chunk = (chunk / wave) * wave;
-    p.chunk = chunk < 1 ? 1 : chunk;
     it = g_plans.emplace(key, p).first;
   }
   *out = &it->second;
   return RAMDSIR_OK;
 }
 
+// Band rows of the planes in flight: one pass over (up to) kChunkPlanes planes at a time, so the workspace stays below
+// 1 GiB however large the batch is.  (Smaller chunks were measured slower: 9-plane chunks 42 k img/s, 18: 65 k, 36: 67 k,
+// whole 192-plane batch 84 k -- the kernels are latency-bound, not DRAM-bound, and fewer, larger launches win.)
 template <class CFG>
-size_t ws_bytes_for(int planes, int chunk) {
-  const int n = planes < chunk ? planes : chunk;
+constexpr int chunk_planes() { return (int)(((size_t)1 << 30) / ((size_t)CFG::nb * CFG::M * 16)); }
+template <class CFG>
+size_t ws_bytes_for(int planes) {
+  const int n = planes < chunk_planes<CFG>() ? planes : chunk_planes<CFG>();
   return (size_t)n * CFG::nb * CFG::M * 16;
 }
 
@@ -253,21 +266,24 @@ int run(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, s
   if (rc) return rc;
   const int planes = nimg * a.C;
   if (planes == 0) return RAMDSIR_OK;
-  const size_t need = ws_bytes_for<CFG>(planes, pl->chunk);
+  const size_t need = ws_bytes_for<CFG>(planes);
   if (ws == nullptr || ws_bytes < need) {
     set_error("multi-pass path needs %zu workspace bytes, got %zu", need, ws_bytes);
     return RAMDSIR_ERR_WORKSPACE;
   }
   float4* Zg = reinterpret_cast<float4*>(ws);
-  for (int p0 = 0; p0 < planes; p0 += pl->chunk) {
-    const int n = (planes - p0 < pl->chunk) ? planes - p0 : pl->chunk;
-    ram_mp_pass_a<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(a.src, Zg, pl->tab_ac, p0);
+  const size_t plane_px = (size_t)CFG::H * CFG::W, patch_px = (size_t)CFG::nb * CFG::nb;
+  for (int p0 = 0; p0 < planes; p0 += chunk_planes<CFG>()) {
+    const int n = (planes - p0 < chunk_planes<CFG>()) ? planes - p0 : chunk_planes<CFG>();
+    // chunks start on image boundaries only if chunk_planes is a multiple of C; pass plane offsets through pointers
+    const float* src = a.src + (size_t)p0 * plane_px;
+    ram_mp_pass_a<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(src, Zg, pl->tab_ac);
     if (bank_mode) {
-      ram_mp_pass_b<CFG, true><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, nullptr, nullptr, nullptr, 10, 0, a.C, bank_out, pl->tab_b, p0);
+      ram_mp_pass_b<CFG, true><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, nullptr, nullptr, nullptr, 10, 0, a.C, bank_out + (size_t)p0 * patch_px, pl->tab_b, 0);
       count_launch(2);
     } else {
       ram_mp_pass_b<CFG, false><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, nullptr, pl->tab_b, p0);
-      ram_mp_pass_c<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(a.src, Zg, a.pidx, a.n_bank, a.C, a.out, a.ep, pl->tab_ac, p0);
+      ram_mp_pass_c<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(src, Zg, a.pidx, a.n_bank, a.C, a.out + (size_t)p0 * plane_px, a.ep, pl->tab_ac, p0);
       count_launch(3);
     }
   }
@@ -283,9 +299,8 @@ bool multipass_supported(int H, int W, int b) {
 size_t multipass_workspace_bytes(int n_images, int C, int H, int W, int b) {
   (void)W; (void)b;
   const int planes = n_images * C;
-  // the chunk size depends on the device's SM count; report the upper bound (72 MB budget / per-plane bytes)
-  if (H == 512) return ws_bytes_for<K512>(planes, (int)((size_t)RAMDSIR_MP_CHUNK_MB * 1024 * 1024 / ((size_t)512 * 512 * 4 + (size_t)K512::nb * K512::M * 16)));
-  return ws_bytes_for<K1024>(planes, (int)((size_t)RAMDSIR_MP_CHUNK_MB * 1024 * 1024 / ((size_t)1024 * 1024 * 4 + (size_t)K1024::nb * K1024::M * 16)));
+  if (planes <= 0) return 0;
+  return H == 512 ? ws_bytes_for<K512>(planes) : ws_bytes_for<K1024>(planes);
 }
 
 int multipass_mix(const MixArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {

@@ -39,7 +39,10 @@ struct KCfg {
   static constexpr int tabBytes = s_al16((tTWP + HP * nb * 2) * 4);
   static constexpr int smemBytes = offTab + tabBytes;
   // pass B shared memory: KG pairs of rows (+kh, -kh) of M float4 (+1 pad), their D rows, tables
-  static constexpr int KG = 4;                                 // kh values per CTA
+#ifndef RD_MP_KG
+#define RD_MP_KG 4
+#endif
+  static constexpr int KG = RD_MP_KG;                          // kh values per CTA
   static constexpr int nkg = (B_ + 1 + KG - 1) / KG;           // CTAs per plane
   static constexpr int SP = N1w + 1;                           // padded pitch of a k2 / j group inside a row: conflict-free
   static constexpr int rowPitch = 16 * SP;                     // float4 per staged row (element c1 + N1w j lives at c1 + SP j)

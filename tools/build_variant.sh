@@ -8,5 +8,5 @@ mkdir -p "$root/gpurun_ab"
 c="$root/ramdsir_b200/csrc"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -t 4 -cudart shared -shared -Xcompiler -fPIC \
      -Xlinker -rpath=/usr/local/cuda/lib64 -o "$root/gpurun_ab/libramdsir_$name.so" \
-     "$c/ramdsir_abi.cu" "$c/ram_fused.cu" "$c/ram_generic.cu" "$c/ram_multipass.cu" "$c/ram_select.cu" "$@"
+     "$c/ramdsir_abi.cu" "$c/ram_fused.cu" "$c/ram_generic.cu" "$c/ram_multipass.cu" "$c/ram_select.cu" "$c/ram_transform.cu" "$@"
 echo "built gpurun_ab/libramdsir_$name.so"
