@@ -455,35 +455,37 @@ def run_ours(args, rank, local_rank, world):
         del s8, want0, got0
 
     # ---- end-to-end through the host-buffer C-ABI entry (pinned host -> device -> pinned host) ----
+    # The fundus loader holds uint8 images at this boundary (PIL -> np.array, BEFORE fundus.py:212's astype(float32)), so the
+    # primary number feeds uint8 host images (ramdsir_mix_host_u8: the kernel widens them, bit-identical to the float32
+    # call); the same call with float32 host images is reported beside it.  Prostate slices are float32 (.npy): f32 only.
     src_h = run.srcs[0].cpu().pin_memory()
     out_h = torch.empty_like(src_h).pin_memory()
     e2e_steps = 1 if args.no_e2e else max(3, min(args.steps, 30))
     chunk = args.e2e_chunk or max(1, min(32, wl.BATCH))          # 32-image chunks measured best (tools/e2e_chunks.py)
-    e2e_u8 = None
     link = None
+    use_u8 = wl.EPI == "fundus"
+    e = run.epi
+    R.ram_mix_batch(run.srcs[0], run.bank, run.pidx, run.rk, L=L, clip=e[:2], scale=e[2], shift=e[3], out=run.outs[0], serial=True)
+    torch.cuda.synchronize()
+    want_h = run.outs[0].cpu()
     with HostPipeline(chunk_images=chunk, C=wl.C, H=wl.H, W=wl.W, L=L) as pipe:
-        for _ in range(3):
-            pipe.mix(src_h, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
-        run._sync()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            pipe.mix(src_h, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
-        e2e_s = time.perf_counter() - t0
-        e = run.epi
-        R.ram_mix_batch(run.srcs[0], run.bank, run.pidx, run.rk, L=L, clip=e[:2], scale=e[2], shift=e[3], out=run.outs[0], serial=True)
-        torch.cuda.synchronize()
-        same = bool(torch.equal(out_h, run.outs[0].cpu()))
-        # same leg with uint8 host images (what a fundus loader holds, fundus.py:212): H2D bytes / 4
-        if wl.EPI == "fundus":
-            src_u8 = src_h.to(torch.uint8).pin_memory()
-            for _ in range(2):
-                pipe.mix(src_u8, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
+        def leg(src):
+            for _ in range(3):
+                pipe.mix(src, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
             run._sync()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                pipe.mix(src_u8, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
-            e2e_u8 = wl.BATCH * world * e2e_steps / run.max_over_ranks(time.perf_counter() - t0)
-    e2e_value = wl.BATCH * world * e2e_steps / run.max_over_ranks(e2e_s)
+                pipe.mix(src, run.bank, run.pidx_h, run.rk_h, out_h, epilogue=run.epi)
+            dt = run.max_over_ranks(time.perf_counter() - t0)
+            return wl.BATCH * world * e2e_steps / dt, bool(torch.equal(out_h, want_h))
+        e2e_f32, same_f32 = leg(src_h)
+        e2e_u8, same_u8 = (None, None)
+        if use_u8:
+            src_u8 = src_h.to(torch.uint8).pin_memory()
+            e2e_u8, same_u8 = leg(src_u8)
+    e2e_value = e2e_u8 if use_u8 else e2e_f32
+    same = same_u8 if use_u8 else same_f32
+    h2d_bytes = int(src_h.numel() * (1 if use_u8 else 4) + run.pidx_h.nbytes + run.rk_h.nbytes)
     if not args.no_e2e:
         # what the host link gives this rank while every rank copies at once: the ceiling of any host-buffer path
         d_in, d_out = run.srcs[0], run.outs[0]
@@ -498,10 +500,18 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
         dt = run.max_over_ranks(time.perf_counter() - t0)
         gbs = 3 * src_h.numel() * 4 / dt / 1e9
-        link = {"h2d_gbs_per_rank": gbs, "d2h_gbs_per_rank": gbs,
-                "ceiling_images_per_s": wl.BATCH * world * 3 / dt,
-                "note": "pinned host <-> device copies of one batch each way, both directions at once, all ranks at once; "
-                        "ceiling = the rate at which batches can cross the host link at all"}
+        run._sync()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            out_h.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt1 = run.max_over_ranks(time.perf_counter() - t0)
+        link = {"both_ways_gbs_per_rank_each_direction": gbs, "d2h_alone_gbs_per_rank": 3 * src_h.numel() * 4 / dt1 / 1e9,
+                "ceiling_images_per_s_float32_in": wl.BATCH * world * 3 / dt,
+                "ceiling_images_per_s_uint8_in": wl.BATCH * world * 3 / dt1,
+                "note": "pinned host <-> device copies of one float32 batch, all ranks at once: both directions together "
+                        "(bounds the float32-in call) and device -> host alone (bounds the uint8-in call, whose upload is 4x "
+                        "smaller); ceiling = the rate at which batches can cross the host link at all"}
     clocks = sampler.stop() if sampler else None
 
     # ---- the other BASELINE configurations, each a few steps ----
@@ -565,12 +575,14 @@ def run_ours(args, rank, local_rank, world):
                 "note": "rank 0, same K steps with RAMDSIR_FLAG_SERIAL (no overlap between steps)"},
             "u8_source": None if u8_src is None else dict(u8_src, frac=u8_src["achieved"] / peak),
             "fft_tflops_nominal": nominal_fft_flops_per_image(wl.C, wl.H, wl.W) * value / 1e12,
-            "e2e": {"value": e2e_value, "unit": "images/s",
-                    "h2d_bytes_per_step": int(src_h.numel() * 4 + run.pidx_h.nbytes + run.rk_h.nbytes),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(out_h.numel() * 4), "steps": e2e_steps, "chunk_images": chunk,
+                    "host_input_dtype": "uint8" if use_u8 else "float32",
                     "matches_device_path": same, "timing": "wall clock around the blocking C-ABI call, max over ranks",
-                    "uint8_input_value": e2e_u8,
-                    "uint8_input_note": "same call with uint8 host images (ramdsir_mix_host_u8): H2D bytes / 4",
+                    "float32_input_value": e2e_f32, "float32_input_matches_device_path": same_f32,
+                    "float32_input_h2d_bytes_per_step": int(src_h.numel() * 4 + run.pidx_h.nbytes + run.rk_h.nbytes),
+                    "note": "ramdsir_mix_host_u8 / _f32: pinned host images -> chunked H2D -> RAM kernel -> chunked D2H -> "
+                            "pinned host float32 output, every step",
                     "host_link": link},
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -355,6 +355,14 @@ def _amp_identity(R, B, C, H, W, nbank, seed):
     i = B // 2
     alone = R.ram_mix_batch(src[i:i + 1].contiguous(), bank, pidx[i:i + 1], rk[i:i + 1])
     assert torch.equal(alone[0], out[i])
+    # and the launch itself against the numpy oracle: 8 images drawn at random FROM the full-size launch
+    pick = np.sort(rs.choice(B, size=min(8, B), replace=False))
+    partners = par[pidx[pick]].cpu().numpy()
+    want = O.mix_batch(src[pick].cpu().numpy(), partners, np.arange(len(pick)), rk[pick].cpu().numpy(), 0.1, epi=None)
+    got = out[pick].cpu().numpy()
+    # no epilogue here: intensities are 0..255, so the tolerance on normalised intensities scales by 127.5
+    r, m = O.rel_l2(got, want), O.max_abs(got, want)
+    assert r <= REL_L2_TOL and m <= MAX_ABS_TOL * 127.5, "sampled images of the full launch: rel_l2=%.3e max_abs=%.3e" % (r, m)
     return out
 
 
