@@ -11,9 +11,7 @@ SIG = [F, F, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int), ct
        ctypes.c_int] * 1 + [ctypes.c_int] * 4 + [ctypes.c_float] * 4 + [F]
 lib.emul_fused.argtypes = SIG
 lib.emul_fused_static.argtypes = SIG
-lib.emul_fused_p2.argtypes = SIG
 lib.emul_multipass.argtypes = SIG
-lib.emul_fused_x2.argtypes = SIG
 
 def ptr(a, t=F): return a.ctypes.data_as(t)
 
@@ -25,8 +23,8 @@ def smooth(rs, c, h, w, lo, hi, integer):
     return (np.round(y) if integer else y).astype(np.float32)
 
 def run(C, H, W, L, epi, rng, B=2, N=3, integer=True, static=False, const_plane=False):
-    fn = {False: lib.emul_fused, True: lib.emul_fused_static, "p2": lib.emul_fused_p2, "mp": lib.emul_multipass, "x2": lib.emul_fused_x2}[static]
-    smem = {False: lib.emul_fused_smem_bytes, True: lib.emul_fused_static_smem_bytes, "p2": lib.emul_fused_p2_smem_bytes, "mp": lambda *a: 0, "x2": lambda *a: 0}[static]
+    fn = {False: lib.emul_fused, True: lib.emul_fused_static, "mp": lib.emul_multipass}[static]
+    smem = {False: lib.emul_fused_smem_bytes, True: lib.emul_fused_static_smem_bytes, "mp": lambda *a: 0}[static]
     lo, hi = (0, 255) if integer else (-1, 1)
     rs = np.random.RandomState(7)
     src = np.stack([smooth(rs, C, H, W, lo, hi, integer) for _ in range(B)])
@@ -34,7 +32,7 @@ def run(C, H, W, L, epi, rng, B=2, N=3, integer=True, static=False, const_plane=
     b = O.band_halfwidth(H, W, L)
     if const_plane:
         src[0, 0] = 77.0
-    print({False: "runtime", True: "static", "p2": "p2", "mp": "multipass", "x2": "x2"}[static], "C,H,W,b", C, H, W, b, "smem", smem(H, W, b))
+    print({False: "runtime", True: "static", "mp": "multipass"}[static], "C,H,W,b", C, H, W, b, "smem", smem(H, W, b))
     bank = np.zeros((N, C, 2*b+1, 2*b+1), np.float32)
     dummy = np.zeros(1, np.float32)
     rc = fn(ptr(par), ptr(dummy), None, None, 10, ptr(dummy), N, C, H, W, b, 0, 0, 0, 0, ptr(bank))
@@ -65,16 +63,8 @@ run(3, 256, 256, 0.1, O.FUNDUS_EPILOGUE, rng, static=True, const_plane=True)
 run(3, 256, 256, 0.1, O.FUNDUS_EPILOGUE, rng, static=False, const_plane=True)
 run(1, 384, 384, 0.1, O.PROSTATE_EPILOGUE, rng, integer=False, static=True, const_plane=True)
 
-run(3, 256, 256, 0.1, O.FUNDUS_EPILOGUE, rng, static="p2")
-run(1, 384, 384, 0.1, O.PROSTATE_EPILOGUE, rng, integer=False, static="p2")
-run(3, 256, 256, 0.1, O.FUNDUS_EPILOGUE, rng, static="p2", const_plane=True)
-run(1, 384, 384, 0.1, O.PROSTATE_EPILOGUE, rng, integer=False, static="p2", const_plane=True)
 
 run(2, 512, 512, 0.1, O.FUNDUS_EPILOGUE, rng, static="mp", B=1, N=2)
 run(1, 1024, 1024, 0.1, O.FUNDUS_EPILOGUE, rng, static="mp", B=1, N=1)
 run(1, 512, 512, 0.1, O.PROSTATE_EPILOGUE, rng, static="mp", B=1, N=1, integer=False, const_plane=True)
 
-run(3, 256, 256, 0.1, O.FUNDUS_EPILOGUE, rng, static="x2")
-run(1, 384, 384, 0.1, O.PROSTATE_EPILOGUE, rng, integer=False, static="x2")
-run(3, 256, 256, 0.1, O.FUNDUS_EPILOGUE, rng, static="x2", const_plane=True)
-run(1, 384, 384, 0.1, O.PROSTATE_EPILOGUE, rng, integer=False, static="x2", const_plane=True)
