@@ -401,6 +401,37 @@ def config_line(run, ms_rank, ms_max, peak, serial_ms=None, extra=None):
     return d
 
 
+def train_step_leg(steps=4):
+    """BASELINE configs[4], second half: one `train.py --ram --rec` step (tools/e2e_step.py restates train.py:223-296 around
+    a small consumer network) fed by the GPU-RAM loader (Fundus_Multi(ram="deferred") + RamBatchHook) and, as the CPU
+    baseline of the same step, by per-sample numpy RAM (the oracle) on identical samples and RNG draws.  Part of the
+    cpu_baseline leg: rank 0, N = 1 only."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import e2e_step as E
+    import fixture_data as FX
+    from oracle import ram_oracle as O
+
+    def oracle_ram(src, partner, k):
+        return O.mix_batch(src[None], partner[None], [0], [k], L, epi=O.FUNDUS_EPILOGUE)[0]
+
+    import contextlib
+    import io
+    with tempfile.TemporaryDirectory(prefix="ramdsir_e2e_") as root, contextlib.redirect_stdout(io.StringIO()):
+        FX.make_fundus(root, counts=E.E2E_FIXTURE)
+        res = E.compare(root, FX.ResizeJitter(), oracle_ram, steps=steps, num_workers=0)
+    d0 = res["diff"][0]
+    return {"batch": res["batch"], "steps": len(res["gpu"]),
+            "loss_step0": res["gpu"][0]["loss"], "loss_rel_diff_step0": d0["loss_rel"], "grad_norm_rel_diff_step0": d0["grad_norm_rel"],
+            "loss_rel_diff_max": max(d["loss_rel"] for d in res["diff"]),
+            "loader_ms_per_step": {"gpu_ram": res["gpu_timing"]["data_ms_per_step"], "cpu_ram": res["cpu_timing"]["data_ms_per_step"]},
+            "model_ms_per_step": res["gpu_timing"]["model_ms_per_step"],
+            "note": "B = 3 + 6 + 7 fundus images per step (train.py:35) from a synthetic on-disk fixture; loader time = sample "
+                    "load + transforms + RAM + H2D for one step, in the main process (num_workers=0); the first step includes "
+                    "one-off table / allocator warm-up"}
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -602,6 +633,8 @@ def run_ours(args, rank, local_rank, world):
                                     "single_core_images_per_s": ips1,
                                     "native_float32_path_images_per_s": ips32,   # what numpy >= 2 does with float32 input
                                     "cpu_model": cpu_model(), "numpy": np.__version__}
+            if not args.no_train_step:
+                line["train_step"] = train_step_leg()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -617,6 +650,7 @@ def main():
     ap.add_argument("--serial", action="store_true", help="RAMDSIR_FLAG_SERIAL on every step (no overlap between steps)")
     ap.add_argument("--no-e2e", action="store_true", help="(dev) shorten the host-buffer end-to-end leg to one step")
     ap.add_argument("--no-configs", action="store_true", help="(dev) skip the extra BASELINE configurations")
+    ap.add_argument("--no-train-step", action="store_true", help="(dev) skip the config-5b train-step leg")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="(dev) images per chunk of the host pipeline")
     ap.add_argument("--workload", default="fundus", choices=sorted(WORKLOADS), help="(dev) default = BASELINE configs[1]")
     args = ap.parse_args()
