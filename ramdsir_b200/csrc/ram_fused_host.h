@@ -108,4 +108,16 @@ inline void fused_tables_fill_static(float* tab) {
     }
 }
 
+// EpiSat parameters of a finite clip range (see ram_fused_static.cuh): computed in double, rounded once.
+inline bool epilogue_sat(const Epilogue& e, EpiSat& s, float& dscale, float& dc_add) {
+  if (!(std::isfinite(e.lo) && std::isfinite(e.hi) && e.hi > e.lo)) return false;
+  const double span = (double)e.hi - (double)e.lo;
+  s.a = (float)(1.0 / span);
+  s.m = (float)(span * (double)e.scale);
+  s.t = (float)((double)e.lo * (double)e.scale + (double)e.shift);
+  dscale = s.a;
+  dc_add = (float)(-(double)e.lo / span);
+  return std::isfinite(s.a) && std::isfinite(s.m) && std::isfinite(s.t);
+}
+
 }  // namespace ramdsir

@@ -35,7 +35,10 @@ struct SCfg {
   static constexpr int offZ = 0;
   static constexpr int zBytes = s_al16(nb * pitchZ * 16);
   static constexpr int eBytes = 8 * N1h * 16 * 16;
-  static constexpr int dBytes = nb * (B_ + 1) * 8;
+  // D[nb][dPitch] float2: an odd pitch keeps the lanes <-> consecutive kh mapping of the band / row tasks free of bank
+  // conflicts (b = 25: pitch 26 float2 = 52 words put lanes l and l + 8 on the same banks)
+  static constexpr int dPitch = (B_ + 1) | 1;
+  static constexpr int dBytes = nb * dPitch * 8;
   static constexpr int pBytes = nb * nb * 4;      // the partner's raw patch
   static constexpr int offE = zBytes, offD = zBytes;   // D aliases E (never live together)
   static constexpr int offTab = zBytes + s_al16(s_max(eBytes, dBytes));
@@ -479,9 +482,9 @@ RD_HD void s_band_mix(unsigned char* sm, const float* patch, float one_minus_rat
       d.im = 0.f;
       d.re += dc_add;
     }
-    D[(size_t)(CFG::nb - 1 - khi) * (CFG::b + 1)] = make_float2(d.re, -d.im);
+    D[(size_t)(CFG::nb - 1 - khi) * CFG::dPitch] = make_float2(d.re, -d.im);
   }
-  D[(size_t)khi * (CFG::b + 1) + kw] = make_float2(d.re, d.im);
+  D[(size_t)khi * CFG::dPitch + kw] = make_float2(d.re, d.im);
 }
 
 template <class CFG>
@@ -499,8 +502,8 @@ template <class CFG>
 RD_HD void s_row_inv(unsigned char* sm, int r) {
   const int khi = r % CFG::nb, c1 = r / CFG::nb;
   const float2* D = reinterpret_cast<const float2*>(sm + CFG::offD);
-  const float2* Dp = D + (size_t)khi * (CFG::b + 1);
-  const float2* Dm = D + (size_t)(CFG::nb - 1 - khi) * (CFG::b + 1);
+  const float2* Dp = D + (size_t)khi * CFG::dPitch;
+  const float2* Dm = D + (size_t)(CFG::nb - 1 - khi) * CFG::dPitch;
   const float4* PT = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tPT) +
                      (size_t)c1 * CFG::nb + CFG::b;
   cf va[16], vb[16];

@@ -5,6 +5,7 @@
 #include <tuple>
 #include <vector>
 #include "ram_internal.h"
+#include "ram_fused_host.h"
 #include "ram_multipass_host.h"
 
 namespace ramdsir {
@@ -52,7 +53,8 @@ template <class CFG, bool BANK, int NT>
 __device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, float4* __restrict__ zplane,
                                           const float* __restrict__ bank, const int64_t* __restrict__ pidx,
                                           const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C,
-                                          float* __restrict__ bank_out, int plane, int gplane, int kg) {
+                                          float* __restrict__ bank_out, int plane, int gplane, int kg,
+                                          float dscale = 1.f, float dc_add = 0.f) {
   constexpr int KG = CFG::KG, M = CFG::M, RP = 2 * CFG::rowPitch, DP = 2 * (CFG::b + 1);
   const int tid = threadIdx.x, kh0 = kg * KG;
   const int ng = (CFG::b + 1 - kh0 < KG) ? CFG::b + 1 - kh0 : KG;     // kh values handled here
@@ -71,7 +73,7 @@ __device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, f
     const int img = gplane / C, ch = gplane - img * C;
     const long long p = pidx[img];
     const bool ok = (p >= 0 && p < (long long)n_bank);
-    omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den : __int_as_float(0x7fc00000);
+    omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den * dscale : __int_as_float(0x7fc00000);
     const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * ((size_t)CFG::nb * CFG::nb);
     float* P = reinterpret_cast<float*>(sm + CFG::bOffP);
     for (int i = tid; i < ng * 2 * CFG::nb; i += NT) {
@@ -96,14 +98,14 @@ __device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, f
     float* patch = bank_out + (size_t)plane * patch_px;
     for (int t = tid; t < ng * nband; t += NT) {
       const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
-      if (live(2 * g + srow)) m_band<CFG, true>(R + (size_t)g * RP, D + g * DP, tab, nullptr, patch, 0.f, kh0 + g, srow, tt % (CFG::b + 1));
+      if (live(2 * g + srow)) m_band<CFG, true>(R + (size_t)g * RP, D + g * DP, tab, nullptr, patch, 0.f, 0.f, kh0 + g, srow, tt % (CFG::b + 1));
     }
   } else {
     {
       const float* P = reinterpret_cast<const float*>(sm + CFG::bOffP);
       for (int t = tid; t < ng * nband; t += NT) {
         const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
-        if (live(2 * g + srow)) m_band<CFG, false>(R + (size_t)g * RP, D + g * DP, tab, P + g * 2 * CFG::nb, nullptr, omr, kh0 + g, srow, tt % (CFG::b + 1));
+        if (live(2 * g + srow)) m_band<CFG, false>(R + (size_t)g * RP, D + g * DP, tab, P + g * 2 * CFG::nb, nullptr, omr, dc_add, kh0 + g, srow, tt % (CFG::b + 1));
       }
     }
     __syncthreads();
@@ -132,10 +134,13 @@ __device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, f
 }
 
 // ---- C: inverse columns of one (plane, strip), + x, epilogue ---------------------------------------------------
-template <class CFG>
+__device__ __forceinline__ EpiClamp mp_poisoned(EpiClamp e) { e.scale = __int_as_float(0x7fc00000); return e; }
+__device__ __forceinline__ EpiSat mp_poisoned(EpiSat e) { e.m = __int_as_float(0x7fc00000); return e; }   // sat() would swallow a NaN
+
+template <class CFG, class EPI>
 __device__ __forceinline__ void mp_task_c(unsigned char* sm, const float* __restrict__ src, const float4* __restrict__ zgp,
                                           const int64_t* __restrict__ pidx, int n_bank, int C, float* __restrict__ out,
-                                          Epilogue ep, int plane, int gplane, int strip, unsigned long long pol_stream) {
+                                          EPI ep, int plane, int gplane, int strip, unsigned long long pol_stream) {
   const int tid = threadIdx.x;
   {
     float4* Zs = reinterpret_cast<float4*>(sm + CFG::offZ);
@@ -144,7 +149,7 @@ __device__ __forceinline__ void mp_task_c(unsigned char* sm, const float* __rest
   }
   {
     const long long p = pidx[gplane / C];
-    if (p < 0 || p >= (long long)n_bank) ep.scale = __int_as_float(0x7fc00000);
+    if (p < 0 || p >= (long long)n_bank) ep = mp_poisoned(ep);
   }
   __syncthreads();
   const size_t plane_px = (size_t)CFG::H * CFG::W;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(256, 2) ram_mp_pass_a(const float* __restrict_
 template <class CFG, bool BANK>
 __global__ void __launch_bounds__(CFG::bThreads) ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank,
     const int64_t* __restrict__ pidx, const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ bank_out,
-    const float* __restrict__ tab_b, int plane0) {
+    const float* __restrict__ tab_b, int plane0, float dscale, float dc_add) {
   extern __shared__ __align__(16) unsigned char sm[];
   const int tid = threadIdx.x, kg = blockIdx.x % CFG::nkg, plane = blockIdx.x / CFG::nkg;
   float4* t = reinterpret_cast<float4*>(sm + CFG::bOffTab);
@@ -191,11 +196,11 @@ __global__ void __launch_bounds__(CFG::bThreads) ram_mp_pass_b(float4* __restric
   // `plane` indexes this chunk's workspace and (bank mode) output; plane0 + plane is the batch-global plane whose
   // image selects the partner and the ratio
   mp_task_b<CFG, BANK, CFG::bThreads>(sm, reinterpret_cast<const float*>(sm + CFG::bOffTab), Zg + (size_t)plane * CFG::nb * CFG::M,
-                                      bank, pidx, rk, ratio_den, n_bank, C, bank_out, plane, plane0 + plane, kg);
+                                      bank, pidx, rk, ratio_den, n_bank, C, bank_out, plane, plane0 + plane, kg, dscale, dc_add);
 }
-template <class CFG>
+template <class CFG, class EPI>
 __global__ void __launch_bounds__(256, 2) ram_mp_pass_c(const float* __restrict__ src, const float4* __restrict__ Zg,
-    const int64_t* __restrict__ pidx, int n_bank, int C, float* __restrict__ out, Epilogue ep, const float* __restrict__ tab_ac, int plane0) {
+    const int64_t* __restrict__ pidx, int n_bank, int C, float* __restrict__ out, EPI ep, const float* __restrict__ tab_ac, int plane0) {
   extern __shared__ __align__(16) unsigned char sm[];
   const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, plane = blockIdx.x / CFG::nstrips;
   float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
@@ -203,8 +208,9 @@ __global__ void __launch_bounds__(256, 2) ram_mp_pass_c(const float* __restrict_
   unsigned long long pol_stream;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
   __syncthreads();
-  mp_task_c<CFG>(sm, src, Zg + (size_t)plane * CFG::nb * CFG::M, pidx, n_bank, C, out, ep, plane, plane0 + plane, strip, pol_stream);
+  mp_task_c<CFG, EPI>(sm, src, Zg + (size_t)plane * CFG::nb * CFG::M, pidx, n_bank, C, out, ep, plane, plane0 + plane, strip, pol_stream);
 }
+
 
 // ---------------------------------------------------------------------------------------------
 namespace {
@@ -239,7 +245,8 @@ int get_plan(MpPlan** out) {
     RD_CUDA(cudaMemcpyAsync(p.tab_b, b.data(), CFG::bTabBytes, cudaMemcpyHostToDevice, up));
     RD_CUDA(cudaStreamSynchronize(up));      // a private stream: nobody else's work is synchronised
     RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_a<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
-    RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_c<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
+    RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_c<CFG, EpiClamp>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
+    RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_c<CFG, EpiSat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
     RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_b<CFG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::bSmemBytes));
     RD_CUDA(cudaFuncSetAttribute(ram_mp_pass_b<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::bSmemBytes));
     it = g_plans.emplace(key, p).first;
@@ -273,17 +280,26 @@ int run(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, s
   }
   float4* Zg = reinterpret_cast<float4*>(ws);
   const size_t plane_px = (size_t)CFG::H * CFG::W, patch_px = (size_t)CFG::nb * CFG::nb;
+  // finite clip range: the two-instruction epilogue of the fused kernels (1 / (hi - lo) folded into dF in pass B)
+  EpiSat es{};
+  float dscale = 1.f, dc_add = 0.f;
+  const bool sat = !bank_mode && epilogue_sat(a.ep, es, dscale, dc_add);
+  if (!sat) { dscale = 1.f; dc_add = 0.f; }
   for (int p0 = 0; p0 < planes; p0 += chunk_planes<CFG>()) {
     const int n = (planes - p0 < chunk_planes<CFG>()) ? planes - p0 : chunk_planes<CFG>();
     // chunks start on image boundaries only if chunk_planes is a multiple of C; pass plane offsets through pointers
     const float* src = a.src + (size_t)p0 * plane_px;
     ram_mp_pass_a<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(src, Zg, pl->tab_ac);
     if (bank_mode) {
-      ram_mp_pass_b<CFG, true><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, nullptr, nullptr, nullptr, 10, 0, a.C, bank_out + (size_t)p0 * patch_px, pl->tab_b, 0);
+      ram_mp_pass_b<CFG, true><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, nullptr, nullptr, nullptr, 10, 0, a.C, bank_out + (size_t)p0 * patch_px, pl->tab_b, 0, 1.f, 0.f);
       count_launch(2);
     } else {
-      ram_mp_pass_b<CFG, false><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, nullptr, pl->tab_b, p0);
-      ram_mp_pass_c<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(src, Zg, a.pidx, a.n_bank, a.C, a.out + (size_t)p0 * plane_px, a.ep, pl->tab_ac, p0);
+      ram_mp_pass_b<CFG, false><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, nullptr, pl->tab_b, p0, dscale, dc_add);
+      if (sat)
+        ram_mp_pass_c<CFG, EpiSat><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(src, Zg, a.pidx, a.n_bank, a.C, a.out + (size_t)p0 * plane_px, es, pl->tab_ac, p0);
+      else
+        ram_mp_pass_c<CFG, EpiClamp><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(src, Zg, a.pidx, a.n_bank, a.C, a.out + (size_t)p0 * plane_px,
+                                                                                     EpiClamp{a.ep.lo, a.ep.hi, a.ep.scale, a.ep.shift}, pl->tab_ac, p0);
       count_launch(3);
     }
   }

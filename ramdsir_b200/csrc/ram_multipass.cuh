@@ -124,24 +124,62 @@ struct MF1Out<CFG, CFG::MM> {
   static RD_HD void run(const cf (&)[4][4], float2*, const float2*, int, bool) {}
 };
 
+// Emit the band rows kh = k2 + 16 K1 from the finished 16-point transform X[k1 mod 16] (at v[pos16(.)]).
+template <class CFG, int K1>
+struct MF1OutFull {
+  static RD_HD void run(const cf (&v)[16], float2* zcol, const float2* twp, int k2, bool first) {
+    const int kh = k2 + 16 * K1;
+    if (kh >= -CFG::b && kh <= CFG::b) {
+      cf o = v[pos16((K1 + 16) & 15)];
+      const float2 w = twp[kh];
+      o = cmul(o, cf{w.x, w.y});
+      float2* z = zcol + (size_t)(kh + CFG::b) * CFG::pitchZ * 2;
+      if (!first) {
+        const float2 old = *z;
+        o = cf{o.re + old.x, o.im + old.y};
+      }
+      *z = make_float2(o.re, o.im);
+    }
+    MF1OutFull<CFG, K1 + 1>::run(v, zcol, twp, k2, first);
+  }
+};
+template <class CFG>
+struct MF1OutFull<CFG, CFG::MM> {
+  static RD_HD void run(const cf (&)[16], float2*, const float2*, int, bool) {}
+};
+
+// Second stage of the 256-row sub-transform.  With a wide band (1024^2: 13 of the 16 residues k1 of every k2 are in
+// the band) the stage is a complete 16-point FFT over h1 -- 64 butterfly additions and 9 twiddles instead of 13
+// four-term twiddled sums; with a narrow band (512^2: 6.4 of 16) the pruned radix-4 + sums form is cheaper.
 template <class CFG>
 RD_HD void m_f1_pruned(unsigned char* sm, int p, int half, int u) {
   const int col = u & 1, c = (u >> 1) & 15, k2l = u >> 5, k2 = 8 * half + k2l;
   const float2* e = reinterpret_cast<const float2*>(sm + CFG::offE) + ((size_t)k2l * 16 * 16 + c) * 2 + col;
-  cf y[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-#pragma unroll
-    for (int bq = 0; bq < 4; ++bq) {
-      const float2 v = e[(a + 4 * bq) * 32];
-      y[a][bq] = cf{v.x, v.y};
-    }
-    fft4<-1>(y[a][0], y[a][1], y[a][2], y[a][3]);
-  }
   float2* zcol = reinterpret_cast<float2*>(sm + CFG::offZ) + c * 2 + col;
   const float2* twp = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWP) +
                       p * CFG::nb + CFG::b;
-  MF1Out<CFG, -CFG::MM>::run(y, zcol, twp, k2, p == 0);
+  if constexpr (CFG::MM >= 6) {
+    cf v[16];
+#pragma unroll
+    for (int h1 = 0; h1 < 16; ++h1) {
+      const float2 t = e[h1 * 32];
+      v[h1] = cf{t.x, t.y};
+    }
+    fft16<-1>(v);
+    MF1OutFull<CFG, -CFG::MM>::run(v, zcol, twp, k2, p == 0);
+  } else {
+    cf y[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int bq = 0; bq < 4; ++bq) {
+        const float2 v = e[(a + 4 * bq) * 32];
+        y[a][bq] = cf{v.x, v.y};
+      }
+      fft4<-1>(y[a][0], y[a][1], y[a][2], y[a][3]);
+    }
+    MF1Out<CFG, -CFG::MM>::run(y, zcol, twp, k2, p == 0);
+  }
 }
 
 // ===== pass C ==================================================================================
@@ -164,13 +202,26 @@ RD_HD void m_inv_pruned(unsigned char* sm, int p, int par, int u) {
     in[i] = v;
   }
   float2* e = reinterpret_cast<float2*>(sm + CFG::offE) + ((size_t)k2l * 16 * 16 + c) * 2 + col;
-  InvA<CFG, 0>::run(in, e);
+  if constexpr (CFG::MM >= 6) {
+    // wide band: a complete inverse 16-point FFT over the residues k1 (those outside [-MM, MM) are zero)
+    cf v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int k1 = k < 8 ? k : k - 16;
+      v[k] = (k1 >= -CFG::MM && k1 < CFG::MM) ? in[k1 + CFG::MM] : cf{0.f, 0.f};
+    }
+    fft16<1>(v);
+#pragma unroll
+    for (int h1 = 0; h1 < 16; ++h1) e[h1 * 32] = make_float2(v[pos16(h1)].re, v[pos16(h1)].im);
+  } else {
+    InvA<CFG, 0>::run(in, e);
+  }
 }
 
 template <class CFG, int J>
 struct MCombine {
-  template <class LoadF4, class StoreF4>
-  static RD_HD void run(LoadF4 ld, StoreF4 st, Epilogue ep, int h1, int p, int c4, const cf (&eva)[8], const cf (&evb)[8],
+  template <class LoadF4, class StoreF4, class EPI>
+  static RD_HD void run(LoadF4 ld, StoreF4 st, EPI ep, int h1, int p, int c4, const cf (&eva)[8], const cf (&evb)[8],
                         const cf (&oda)[8], const cf (&odb)[8]) {
     const cf wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
     const cf ea = eva[pos8(J)], eb = evb[pos8(J)];
@@ -179,20 +230,15 @@ struct MCombine {
       const size_t off = (size_t)((h1 + 16 * (J + 8 * hi)) * CFG::HP + p) * CFG::M + c4;
       const cf a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
       const float4 x = ld(off);
-      float4 y;
-      y.x = fmaf(fminf(fmaxf(x.x + a.re, ep.lo), ep.hi), ep.scale, ep.shift);
-      y.y = fmaf(fminf(fmaxf(x.y + bq.re, ep.lo), ep.hi), ep.scale, ep.shift);
-      y.z = fmaf(fminf(fmaxf(x.z + a.im, ep.lo), ep.hi), ep.scale, ep.shift);
-      y.w = fmaf(fminf(fmaxf(x.w + bq.im, ep.lo), ep.hi), ep.scale, ep.shift);
-      st(off, y);
+      st(off, make_float4(ep(x.x, a.re), ep(x.y, bq.re), ep(x.z, a.im), ep(x.w, bq.im)));
     }
     MCombine<CFG, J + 1>::run(ld, st, ep, h1, p, c4, eva, evb, oda, odb);
   }
 };
 template <class CFG>
 struct MCombine<CFG, 8> {
-  template <class LoadF4, class StoreF4>
-  static RD_HD void run(LoadF4, StoreF4, Epilogue, int, int, int, const cf (&)[8], const cf (&)[8], const cf (&)[8], const cf (&)[8]) {}
+  template <class LoadF4, class StoreF4, class EPI>
+  static RD_HD void run(LoadF4, StoreF4, EPI, int, int, int, const cf (&)[8], const cf (&)[8], const cf (&)[8], const cf (&)[8]) {}
 };
 
 // ===== pass B ==================================================================================
@@ -259,7 +305,7 @@ RD_HD int m_slot(int kw) {
 // Band task: bin (s kh, kw), kw in [0, b], s = +1 (row 0 = +kh) or -1 (row 1 = -kh).  Writes D[s][kw].
 template <class CFG, bool BANK>
 RD_HD void m_band(const float4* R, float2* D, const float* tab, const float* patch, float* patch_out, float one_minus_ratio,
-                  int kh, int srow, int kw) {
+                  float dc_add, int kh, int srow, int kw) {
   const int khs = srow ? -kh : kh;
   const float4 up4 = R[(size_t)srow * CFG::rowPitch + m_slot<CFG>(kw)];
   const float4 um4 = R[(size_t)(kh == 0 ? 0 : 1 - srow) * CFG::rowPitch + m_slot<CFG>(-kw)];
@@ -290,7 +336,10 @@ RD_HD void m_band(const float4* R, float2* D, const float* tab, const float* pat
   } else {
     d = cf{one_minus_ratio * at * CFG::invHW, 0.f};
   }
-  if (kw == 0 && kh == 0) d.im = 0.f;
+  if (kw == 0 && kh == 0) {
+    d.im = 0.f;
+    d.re += dc_add;          // EpiSat: -lo / (hi - lo) on every pixel of delta (see ram_fused_static.cuh)
+  }
   D[srow * (CFG::b + 1) + kw] = make_float2(d.re, d.im);
 }
 

@@ -206,7 +206,7 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
         for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, -1>(R, t);
         if (bank_out) {
           for (int t = 0; t < nrows * (CFG::b + 1); ++t)
-            m_band<CFG, true>(R, D, tab, nullptr, bank_out + pl * psz, 0.f, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+            m_band<CFG, true>(R, D, tab, nullptr, bank_out + pl * psz, 0.f, 0.f, kh, t / (CFG::b + 1), t % (CFG::b + 1));
           continue;
         }
         std::vector<float> prow(2 * CFG::nb);
@@ -215,7 +215,7 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
           prow[CFG::nb + j] = patch[(size_t)(CFG::b - kh) * CFG::nb + j];
         }
         for (int t = 0; t < nrows * (CFG::b + 1); ++t)
-          m_band<CFG, false>(R, D, tab, prow.data(), nullptr, omr, kh, t / (CFG::b + 1), t % (CFG::b + 1));
+          m_band<CFG, false>(R, D, tab, prow.data(), nullptr, omr, 0.f, kh, t / (CFG::b + 1), t % (CFG::b + 1));
         for (int t = 0; t < 2 * CFG::rowPitch; ++t) R[t] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < nrows * CFG::nb; ++t) m_put_v<CFG>(R, D, tab, kh, t / CFG::nb, t % CFG::nb);
         for (int t = 0; t < nrows * 16; ++t) m_row_stage2<CFG, 1>(R, t);
@@ -240,7 +240,7 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
           }
           for (int t = 0; t < 256; ++t) {
             cf* r = &regs[(size_t)t * 32];
-            MCombine<CFG, 0>::run(ld, st, ep, t >> 4, p, strip * 16 + (t & 15), *reinterpret_cast<cf(*)[8]>(r),
+            MCombine<CFG, 0>::run(ld, st, EpiClamp{ep.lo, ep.hi, ep.scale, ep.shift}, t >> 4, p, strip * 16 + (t & 15), *reinterpret_cast<cf(*)[8]>(r),
                                   *reinterpret_cast<cf(*)[8]>(r + 8), *reinterpret_cast<cf(*)[8]>(r + 16), *reinterpret_cast<cf(*)[8]>(r + 24));
           }
         }
