@@ -233,18 +233,18 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
       float4 lo[8];
       s_f1_load_rows<CFG, 0>(ld_first, 0, tid, lo);
       for (int strip = 0; strip < CFG::nstrips; ++strip) {
-        cf va[16], vb[16];
+        cf2 v[16];
         {
           float4 hi[8];
           s_f1_load_rows<CFG, 8>(ld_first, strip, tid, hi);
           if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
-          s_f1_fft_tw_raw<CFG>(sm, tid, lo, hi, va, vb);
+          s_f1_fft_tw_raw_x2<CFG>(sm, tid, lo, hi, v);
         }
-        s_f1_store_half<CFG>(sm, tid, 0, va, vb);
+        s_f1_store_half_x2<CFG>(sm, tid, 0, v);
         __syncthreads();
         for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, 0, u);
         __syncthreads();
-        s_f1_store_half<CFG>(sm, tid, 1, va, vb);
+        s_f1_store_half_x2<CFG>(sm, tid, 1, v);
         if (strip + 1 < CFG::nstrips) s_f1_load_rows<CFG, 0>(ld_first, strip + 1, tid, lo);
         __syncthreads();
         for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, 1, u);
@@ -252,12 +252,12 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
       }
     } else {
       for (int strip = 0; strip < CFG::nstrips; ++strip) {
-        cf va[16], vb[16];
-        s_f1_load_fft_tw<CFG>(ld_first, sm, strip, tid, va, vb);
+        cf2 v[16];
+        s_f1_load_fft_tw_x2<CFG>(ld_first, sm, strip, tid, v);
         if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          s_f1_store_half<CFG>(sm, tid, half, va, vb);
+          s_f1_store_half_x2<CFG>(sm, tid, half, v);
           __syncthreads();
           for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, half, u);
           __syncthreads();

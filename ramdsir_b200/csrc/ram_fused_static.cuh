@@ -15,6 +15,7 @@
 //   sum over a for the k1 in [-MM, MM-1] whose kh lies in the band.
 #pragma once
 #include "ram_fused_core.cuh"
+#include "ram_math_x2.cuh"
 
 namespace ramdsir {
 
@@ -123,6 +124,51 @@ RD_HD void s_f1_fft_tw_raw(const unsigned char* sm, int t, const float4 (&lo)[8]
     }
     va[pos16(2 * i + 1)] = cmul(va[pos16(2 * i + 1)], cf{w.z, w.w});
     vb[pos16(2 * i + 1)] = cmul(vb[pos16(2 * i + 1)], cf{w.z, w.w});
+  }
+}
+
+// ---- packed-pair (FADD2 / FMUL2 / FFMA2) versions of F1a / F1b: the two packed columns of a thread travel as
+// register pairs through the radix-16 and the TWH twiddles at half the issue slots (this phase is issue-bound once its
+// loads have landed); E keeps its layout, at the price of two or three MOVs per published float4.  Measured on B200:
+// +1.2 % (256^2), +3.2 % (384^2).  The same treatment of the inverse second stage (+0.6 % / -7.5 %) and of the row
+// transforms (-1 % / -1.8 %) does not pay: those phases wait on shared memory and barriers, not on issue slots, and
+// the pair <-> (re, im) permutes around their LDS / STS cost more than the arithmetic they save.
+template <class CFG>
+RD_HD void s_f1_fft_tw_x2(const unsigned char* sm, int t, cf2 (&v)[16]) {
+  const int h1 = t >> 4;
+  fft16x<-1>(v);
+  const float4* tw = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWH) +
+                     h1 * (CFG::twhPitch / 2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 w = tw[i];
+    if (i > 0) v[pos16(2 * i)] = cmul2(v[pos16(2 * i)], f2_bcast(w.x), f2_bcast(w.y));
+    v[pos16(2 * i + 1)] = cmul2(v[pos16(2 * i + 1)], f2_bcast(w.z), f2_bcast(w.w));
+  }
+}
+template <class CFG, class LoadF4>
+RD_HD void s_f1_load_fft_tw_x2(LoadF4 ld, const unsigned char* sm, int strip, int t, cf2 (&v)[16]) {
+  const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = cf2_from(ld((size_t)(h1 + CFG::N1h * j) * CFG::M + c4));
+  s_f1_fft_tw_x2<CFG>(sm, t, v);
+}
+template <class CFG>
+RD_HD void s_f1_fft_tw_raw_x2(const unsigned char* sm, int t, const float4 (&lo)[8], const float4 (&hi)[8], cf2 (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = cf2_from(lo[j]);
+    v[j + 8] = cf2_from(hi[j]);
+  }
+  s_f1_fft_tw_x2<CFG>(sm, t, v);
+}
+template <class CFG>
+RD_HD void s_f1_store_half_x2(unsigned char* sm, int t, int half, const cf2 (&v)[16]) {
+  float4* E = reinterpret_cast<float4*>(sm + CFG::offE) + (t >> 4) * 16 + (t & 15);
+#pragma unroll
+  for (int k2l = 0; k2l < 8; ++k2l) {
+    const cf2 a = half ? v[pos16(8 + k2l)] : v[pos16(k2l)];
+    E[k2l * CFG::N1h * 16] = make_float4(f2_lo(a.re), f2_lo(a.im), f2_hi(a.re), f2_hi(a.im));
   }
 }
 

@@ -32,11 +32,11 @@ __device__ __forceinline__ void mp_task_a(unsigned char* sm, const float* __rest
   const float4* x4 = reinterpret_cast<const float4*>(src + (size_t)plane * CFG::H * CFG::W);
   auto ld = [&](size_t off) { return mp_ldg_policy(x4 + off, pol_keep); };
   for (int p = 0; p < CFG::HP; ++p) {
-    cf va[16], vb[16];
-    m_f1_load_fft_tw<CFG>(ld, sm, strip, p, tid, va, vb);
+    cf2 v[16];
+    m_f1_load_fft_tw_x2<CFG>(ld, sm, strip, p, tid, v);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      s_f1_store_half<CFG>(sm, tid, half, va, vb);
+      s_f1_store_half_x2<CFG>(sm, tid, half, v);
       __syncthreads();
       m_f1_pruned<CFG>(sm, p, half, tid);
       __syncthreads();

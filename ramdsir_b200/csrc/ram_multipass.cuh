@@ -101,6 +101,15 @@ RD_HD void m_f1_load_fft_tw(LoadF4 ld, const unsigned char* sm, int strip, int p
   }
 }
 
+// packed-pair version (see s_f1_fft_tw_x2): the radix-16 and the TWH twiddles on register pairs
+template <class CFG, class LoadF4>
+RD_HD void m_f1_load_fft_tw_x2(LoadF4 ld, const unsigned char* sm, int strip, int p, int t, cf2 (&v)[16]) {
+  const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = cf2_from(ld((size_t)((h1 + 16 * j) * CFG::HP + p) * CFG::M + c4));
+  s_f1_fft_tw_x2<CFG>(sm, t, v);
+}
+
 template <class CFG, int K1>
 struct MF1Out {   // Zs[kh] (+)= TWP[p][kh] * sum_a W_16^(a k1) y[a][k1 mod 4]
   static RD_HD void run(const cf (&y)[4][4], float2* zcol, const float2* twp, int k2, bool first) {

@@ -88,9 +88,12 @@ static void run_plane_static(unsigned char* sm, const float* x, const float* pat
   auto A = [&](int t) -> cf(&)[16] { return *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]); };
   auto Bv = [&](int t) -> cf(&)[16] { return *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32 + 16]); };
   for (int strip = 0; strip < CFG::nstrips; ++strip) {
-    for (int t = 0; t < NT; ++t) s_f1_load_fft_tw<CFG>(ld, sm, strip, t, A(t), Bv(t));
+    // the kernel's packed-pair forward stage (host definitions of FADD2 / FMUL2 / FFMA2: lane by lane)
+    auto V = [&](int t) -> cf2(&)[16] { return *reinterpret_cast<cf2(*)[16]>(&regs[(size_t)t * 32]); };
+    static_assert(sizeof(cf2) == 2 * sizeof(cf), "a thread's 16 packed pairs fill its 32 emulated complex registers");
+    for (int t = 0; t < NT; ++t) s_f1_load_fft_tw_x2<CFG>(ld, sm, strip, t, V(t));
     for (int half = 0; half < 2; ++half) {
-      for (int t = 0; t < NT; ++t) s_f1_store_half<CFG>(sm, t, half, A(t), Bv(t));
+      for (int t = 0; t < NT; ++t) s_f1_store_half_x2<CFG>(sm, t, half, V(t));
       for (int u = 0; u < 256; ++u) s_f1_pruned<CFG>(sm, strip, half, u);
     }
   }
