@@ -313,7 +313,7 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
       };
       const int next = plane + gridDim.x;
       for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
-        cf eva[8], evb[8], oda[8], odb[8];
+        typename CFG::cx_fft8 eva[8], evb[8], oda[8], odb[8];
         if (strip > 0) prefetch_strip<CFG>(x4, strip - 1, tid, true);
         else if (next < nplanes) prefetch_strip<CFG>(reinterpret_cast<const Quad*>(src + next * plane_px), 0, tid);
         for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 0, u);

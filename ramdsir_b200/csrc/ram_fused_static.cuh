@@ -14,6 +14,7 @@
 //   fft16 over j (registers) -> twiddle table TWH[h1][k2] -> exchange through E -> fft4 over b' ->
 //   sum over a for the k1 in [-MM, MM-1] whose kh lies in the band.
 #pragma once
+#include <type_traits>
 #include "ram_fused_core.cuh"
 #include "ram_math_x2.cuh"
 
@@ -61,6 +62,39 @@ struct SCfg {
   static constexpr int offBar = offTab + tabBytes;      // two mbarriers (tables, patch)
   static constexpr int smemBytes = offBar + 16;
   static constexpr float invHW = (float)(1.0 / ((double)H_ * (double)W_));
+  // Complex arithmetic of each phase: cf = scalar FADD / FMUL / FFMA, cp = (re, im) register pairs on FADD2 / FMUL2 /
+  // FFMA2 (ram_math_x2.cuh): half the issue slots for the same FP-pipe time -- and scalar butterflies can use both FP
+  // pipes while packed ones cannot (tools/microbench/pipes.cu: 321 vs 243 lane-ops/ns/SM), so packing pays only where
+  // a phase is short of issue slots.  Measured phase by phase on B200 (kernel time, 256^2 with two CTAs per SM / 384^2
+  // with one): second stage of the forward columns +-0 / -0.8 %, first stage of the inverse columns +-0 / -5.7 %,
+  // second stage of the inverse columns + combine +1.35 % / -6.5 %, row transforms -0.3 % / -2.9 %, band bins -0.2 % /
+  // +0.3 %.  (-DRD_CX_<PHASE>=cp|cf overrides a phase for such A/B runs.)
+  static constexpr bool kTwoCtas = (H_ * W_ <= 256 * 256);
+#ifdef RD_CX_F1P
+  using cx_f1p = RD_CX_F1P;
+#else
+  using cx_f1p = cf;             // forward columns, second stage
+#endif
+#ifdef RD_CX_INVP
+  using cx_invp = RD_CX_INVP;
+#else
+  using cx_invp = cf;            // inverse columns, first stage
+#endif
+#ifdef RD_CX_FFT8
+  using cx_fft8 = RD_CX_FFT8;
+#else
+  using cx_fft8 = typename std::conditional<kTwoCtas, cp, cf>::type;   // inverse columns, second stage + combine
+#endif
+#ifdef RD_CX_ROW
+  using cx_row = RD_CX_ROW;
+#else
+  using cx_row = cf;             // row transforms
+#endif
+#ifdef RD_CX_BAND
+  using cx_band = RD_CX_BAND;
+#else
+  using cx_band = cf;            // band bins (one output of an N1w-point butterfly)
+#endif
   static_assert(H_ % 64 == 0 && W_ % 64 == 0, "static fused path needs H, W multiples of 64");
   static_assert(2 * B_ + 1 <= M && 2 * B_ + 1 <= H_, "band must fit the packed spectrum");
   static_assert(nthreads >= 256 && nthreads <= 512, "block size out of range");
@@ -187,44 +221,48 @@ RD_HD void s_f1_store_half(unsigned char* sm, int t, int half, const cf (&va)[16
 // second stage of the pruned N1h-point transform: out = sum_a W_N1h^(DIR a k1) y[a]
 template <class CFG, int K1, int DIR, int A>
 struct SumA {
-  static RD_HD cf run(const cf (&y)[CFG::Q][4]) {
+  template <class CX>
+  static RD_HD CX run(const CX (&y)[CFG::Q][4]) {
     constexpr int r = ((K1 % 4) + 4) % 4;
     return SumA<CFG, K1, DIR, A - 1>::run(y) + twidN<CFG::N1h, A * K1, DIR>(y[A][r]);
   }
 };
 template <class CFG, int K1, int DIR>
 struct SumA<CFG, K1, DIR, 0> {
-  static RD_HD cf run(const cf (&y)[CFG::Q][4]) { return y[0][((K1 % 4) + 4) % 4]; }
+  template <class CX>
+  static RD_HD CX run(const CX (&y)[CFG::Q][4]) { return y[0][((K1 % 4) + 4) % 4]; }
 };
 
 template <class CFG, int K1>
 struct F1Out {   // emits band rows kh = k2 + 16 k1 for k1 = K1 .. MM-1
-  static RD_HD void run(const cf (&y)[CFG::Q][4], float2* zcol, int k2) {
+  template <class CX>
+  static RD_HD void run(const CX (&y)[CFG::Q][4], float2* zcol, int k2) {
     const int kh = k2 + 16 * K1;
     if (kh >= -CFG::b && kh <= CFG::b) {
-      const cf o = SumA<CFG, K1, -1, CFG::Q - 1>::run(y);
-      zcol[(size_t)(kh + CFG::b) * CFG::pitchZ * 2] = make_float2(o.re, o.im);
+      const CX o = SumA<CFG, K1, -1, CFG::Q - 1>::run(y);
+      zcol[(size_t)(kh + CFG::b) * CFG::pitchZ * 2] = make_float2(cx_re(o), cx_im(o));
     }
     F1Out<CFG, K1 + 1>::run(y, zcol, k2);
   }
 };
 template <class CFG>
 struct F1Out<CFG, CFG::MM> {
-  static RD_HD void run(const cf (&)[CFG::Q][4], float2*, int) {}
+  template <class CX>
+  static RD_HD void run(const CX (&)[CFG::Q][4], float2*, int) {}
 };
 
 // ---- F1c: task u = (col = u & 1, c = (u >> 1) & 15, k2l = u >> 5): pruned N1h-point DFT over h1 -----
-template <class CFG>
+template <class CFG, class CX = typename CFG::cx_f1p>
 RD_HD void s_f1_pruned(unsigned char* sm, int strip, int half, int u) {
   const int col = u & 1, c = (u >> 1) & 15, k2l = u >> 5, k2 = 8 * half + k2l;
   const float2* e = reinterpret_cast<const float2*>(sm + CFG::offE) + ((size_t)k2l * CFG::N1h * 16 + c) * 2 + col;
-  cf y[CFG::Q][4];
+  CX y[CFG::Q][4];
 #pragma unroll
   for (int a = 0; a < CFG::Q; ++a) {
 #pragma unroll
     for (int bq = 0; bq < 4; ++bq) {
       const float2 v = e[(a + CFG::Q * bq) * 32];
-      y[a][bq] = cf{v.x, v.y};
+      y[a][bq] = cx_make<CX>(v.x, v.y);
     }
     fft4<-1>(y[a][0], y[a][1], y[a][2], y[a][3]);
   }
@@ -236,8 +274,8 @@ RD_HD void s_f1_pruned(unsigned char* sm, int strip, int half, int u) {
 // E'[k2l][h1][c].col = sum_k1 z'[k2 + 16 k1][c].col W_N1h^(-h1 k1)
 template <class CFG, int K1>
 struct InvGather {   // t[r] += in[k1] * W_N1h^(+a k1), for k1 = K1 .. MM-1
-  template <int A>
-  static RD_HD void run(const cf (&in)[2 * CFG::MM], cf (&t)[4]) {
+  template <int A, class CX>
+  static RD_HD void run(const CX (&in)[2 * CFG::MM], CX (&t)[4]) {
     constexpr int r = ((K1 % 4) + 4) % 4;
     t[r] = t[r] + twidN<CFG::N1h, A * K1, 1>(in[K1 + CFG::MM]);
     InvGather<CFG, K1 + 1>::template run<A>(in, t);
@@ -245,38 +283,40 @@ struct InvGather {   // t[r] += in[k1] * W_N1h^(+a k1), for k1 = K1 .. MM-1
 };
 template <class CFG>
 struct InvGather<CFG, CFG::MM> {
-  template <int A>
-  static RD_HD void run(const cf (&)[2 * CFG::MM], cf (&)[4]) {}
+  template <int A, class CX>
+  static RD_HD void run(const CX (&)[2 * CFG::MM], CX (&)[4]) {}
 };
 
 template <class CFG, int A>
 struct InvA {   // for a = A .. Q-1
-  static RD_HD void run(const cf (&in)[2 * CFG::MM], float2* e) {
-    cf t[4] = {cf{0.f, 0.f}, cf{0.f, 0.f}, cf{0.f, 0.f}, cf{0.f, 0.f}};
+  template <class CX>
+  static RD_HD void run(const CX (&in)[2 * CFG::MM], float2* e) {
+    CX t[4] = {cx_make<CX>(0.f, 0.f), cx_make<CX>(0.f, 0.f), cx_make<CX>(0.f, 0.f), cx_make<CX>(0.f, 0.f)};
     InvGather<CFG, -CFG::MM>::template run<A>(in, t);
     fft4<1>(t[0], t[1], t[2], t[3]);
 #pragma unroll
-    for (int bq = 0; bq < 4; ++bq) e[(A + CFG::Q * bq) * 32] = make_float2(t[bq].re, t[bq].im);
+    for (int bq = 0; bq < 4; ++bq) e[(A + CFG::Q * bq) * 32] = make_float2(cx_re(t[bq]), cx_im(t[bq]));
     InvA<CFG, A + 1>::run(in, e);
   }
 };
 template <class CFG>
 struct InvA<CFG, CFG::Q> {
-  static RD_HD void run(const cf (&)[2 * CFG::MM], float2*) {}
+  template <class CX>
+  static RD_HD void run(const CX (&)[2 * CFG::MM], float2*) {}
 };
 
-template <class CFG>
+template <class CFG, class CX = typename CFG::cx_invp>
 RD_HD void s_inv_pruned(unsigned char* sm, int strip, int par, int u) {
   const int col = u & 1, c = (u >> 1) & 15, k2l = u >> 5, k2 = 2 * k2l + par;
   const float2* zcol = reinterpret_cast<const float2*>(sm + CFG::offZ) + (strip * 16 + c) * 2 + col;
-  cf in[2 * CFG::MM];
+  CX in[2 * CFG::MM];
 #pragma unroll
   for (int i = 0; i < 2 * CFG::MM; ++i) {
     const int kh = k2 + 16 * (i - CFG::MM);
-    cf v{0.f, 0.f};
+    CX v = cx_make<CX>(0.f, 0.f);
     if (kh >= -CFG::b && kh <= CFG::b) {
       const float2 z = zcol[(size_t)(kh + CFG::b) * CFG::pitchZ * 2];
-      v = cf{z.x, z.y};
+      v = cx_make<CX>(z.x, z.y);
     }
     in[i] = v;
   }
@@ -286,8 +326,8 @@ RD_HD void s_inv_pruned(unsigned char* sm, int strip, int par, int u) {
 
 // ---- inverse, second stage part 1: thread (h1, c) takes the 8 k2 of one parity from E', applies
 // conj(TWH[h1][k2]) and a radix-8 inverse; results stay in registers until both parities are done ----
-template <class CFG>
-RD_HD void s_inv_fft8(const unsigned char* sm, int t, int par, cf (&pa)[8], cf (&pb)[8]) {
+template <class CFG, class CX>
+RD_HD void s_inv_fft8(const unsigned char* sm, int t, int par, CX (&pa)[8], CX (&pb)[8]) {
   const int h1 = t >> 4;
   const float4* E = reinterpret_cast<const float4*>(sm + CFG::offE) + h1 * 16 + (t & 15);
   const float2* tw = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWH) +
@@ -296,8 +336,8 @@ RD_HD void s_inv_fft8(const unsigned char* sm, int t, int par, cf (&pa)[8], cf (
   for (int m = 0; m < 8; ++m) {
     const float4 v = E[m * CFG::N1h * 16];
     const float2 w = tw[2 * m];
-    pa[m] = cmulc(cf{v.x, v.y}, cf{w.x, w.y});
-    pb[m] = cmulc(cf{v.z, v.w}, cf{w.x, w.y});
+    pa[m] = cmulc(cx_make<CX>(v.x, v.y), cf{w.x, w.y});
+    pb[m] = cmulc(cx_make<CX>(v.z, v.w), cf{w.x, w.y});
   }
   fft8<1>(pa);
   fft8<1>(pb);
@@ -330,17 +370,17 @@ struct EpiSat {
 template <class CFG, int J>
 struct Combine {
   // `st(off, y, x)`: y is the augmented pixel quad, x the source quad just read (for the fused dual output)
-  template <class LoadF4, class StoreF4, class EPI>
-  static RD_HD void run(LoadF4 ld, StoreF4 st, EPI ep, size_t base, const cf (&eva)[8], const cf (&evb)[8],
-                        const cf (&oda)[8], const cf (&odb)[8]) {
-    const cf wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
-    const cf ea = eva[pos8(J)], eb = evb[pos8(J)];
+  template <class LoadF4, class StoreF4, class EPI, class CX>
+  static RD_HD void run(LoadF4 ld, StoreF4 st, EPI ep, size_t base, const CX (&eva)[8], const CX (&evb)[8],
+                        const CX (&oda)[8], const CX (&odb)[8]) {
+    const CX wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
+    const CX ea = eva[pos8(J)], eb = evb[pos8(J)];
 #pragma unroll
     for (int hi = 0; hi < 2; ++hi) {
       const size_t off = base + (size_t)(CFG::N1h * (J + 8 * hi)) * CFG::M;
-      const cf a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
+      const CX a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
       const float4 x = ld(off);
-      const float4 y = make_float4(ep(x.x, a.re), ep(x.y, bq.re), ep(x.z, a.im), ep(x.w, bq.im));
+      const float4 y = make_float4(ep(x.x, cx_re(a)), ep(x.y, cx_re(bq)), ep(x.z, cx_im(a)), ep(x.w, cx_im(bq)));
       st(off, y, x);
     }
     Combine<CFG, J + 1>::run(ld, st, ep, base, eva, evb, oda, odb);
@@ -348,24 +388,24 @@ struct Combine {
 };
 template <class CFG>
 struct Combine<CFG, 8> {
-  template <class LoadF4, class StoreF4, class EPI>
-  static RD_HD void run(LoadF4, StoreF4, EPI, size_t, const cf (&)[8], const cf (&)[8], const cf (&)[8], const cf (&)[8]) {}
+  template <class LoadF4, class StoreF4, class EPI, class CX>
+  static RD_HD void run(LoadF4, StoreF4, EPI, size_t, const CX (&)[8], const CX (&)[8], const CX (&)[8], const CX (&)[8]) {}
 };
 
 // Variant with the x quads of rows J = 0..3 (both halves) preloaded one stage early (xpre[2 J + hi]).
 template <class CFG, int J>
 struct CombineP {
-  template <class LoadF4, class StoreF4, class EPI>
-  static RD_HD void run(LoadF4 ld, StoreF4 st, EPI ep, size_t base, const float4 (&xpre)[8], const cf (&eva)[8],
-                        const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
-    const cf wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
-    const cf ea = eva[pos8(J)], eb = evb[pos8(J)];
+  template <class LoadF4, class StoreF4, class EPI, class CX>
+  static RD_HD void run(LoadF4 ld, StoreF4 st, EPI ep, size_t base, const float4 (&xpre)[8], const CX (&eva)[8],
+                        const CX (&evb)[8], const CX (&oda)[8], const CX (&odb)[8]) {
+    const CX wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
+    const CX ea = eva[pos8(J)], eb = evb[pos8(J)];
 #pragma unroll
     for (int hi = 0; hi < 2; ++hi) {
       const size_t off = base + (size_t)(CFG::N1h * (J + 8 * hi)) * CFG::M;
-      const cf a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
+      const CX a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
       const float4 x = (J < 4) ? xpre[2 * (J & 3) + hi] : ld(off);
-      const float4 y = make_float4(ep(x.x, a.re), ep(x.y, bq.re), ep(x.z, a.im), ep(x.w, bq.im));
+      const float4 y = make_float4(ep(x.x, cx_re(a)), ep(x.y, cx_re(bq)), ep(x.z, cx_im(a)), ep(x.w, cx_im(bq)));
       st(off, y, x);
     }
     CombineP<CFG, J + 1>::run(ld, st, ep, base, xpre, eva, evb, oda, odb);
@@ -373,9 +413,9 @@ struct CombineP {
 };
 template <class CFG>
 struct CombineP<CFG, 8> {
-  template <class LoadF4, class StoreF4, class EPI>
-  static RD_HD void run(LoadF4, StoreF4, EPI, size_t, const float4 (&)[8], const cf (&)[8], const cf (&)[8],
-                        const cf (&)[8], const cf (&)[8]) {}
+  template <class LoadF4, class StoreF4, class EPI, class CX>
+  static RD_HD void run(LoadF4, StoreF4, EPI, size_t, const float4 (&)[8], const CX (&)[8], const CX (&)[8],
+                        const CX (&)[8], const CX (&)[8]) {}
 };
 
 template <class CFG, class LoadF4>
@@ -385,16 +425,16 @@ RD_HD void s_inv_preload_x(LoadF4 ld, int strip, int t, float4 (&xpre)[8]) {
   for (int i = 0; i < 8; ++i) xpre[i] = ld(base + (size_t)(CFG::N1h * ((i >> 1) + 8 * (i & 1))) * CFG::M);
 }
 
-template <class CFG, class LoadF4, class StoreF4, class EPI>
+template <class CFG, class LoadF4, class StoreF4, class EPI, class CX>
 RD_HD void s_inv_combine_store_pre(LoadF4 ld, StoreF4 st, EPI ep, int strip, int t, const float4 (&xpre)[8],
-                                   const cf (&eva)[8], const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
+                                   const CX (&eva)[8], const CX (&evb)[8], const CX (&oda)[8], const CX (&odb)[8]) {
   const size_t base = (size_t)(t >> 4) * CFG::M + strip * 16 + (t & 15);
   CombineP<CFG, 0>::run(ld, st, ep, base, xpre, eva, evb, oda, odb);
 }
 
-template <class CFG, class LoadF4, class StoreF4, class EPI>
-RD_HD void s_inv_combine_store(LoadF4 ld, StoreF4 st, EPI ep, int strip, int t, const cf (&eva)[8],
-                               const cf (&evb)[8], const cf (&oda)[8], const cf (&odb)[8]) {
+template <class CFG, class LoadF4, class StoreF4, class EPI, class CX>
+RD_HD void s_inv_combine_store(LoadF4 ld, StoreF4 st, EPI ep, int strip, int t, const CX (&eva)[8],
+                               const CX (&evb)[8], const CX (&oda)[8], const CX (&odb)[8]) {
   const size_t base = (size_t)(t >> 4) * CFG::M + strip * 16 + (t & 15);
   Combine<CFG, 0>::run(ld, st, ep, base, eva, evb, oda, odb);
 }
@@ -408,16 +448,16 @@ RD_HD void s_inv_combine_store(LoadF4 ld, StoreF4 st, EPI ep, int strip, int t, 
 // row_fwd does the radix-16 over j and the twiddle TWM[c1][k2]; the band task finishes with ONE
 // output of an N1w-point butterfly (exact +-1, +-i for N1w = 4; radix-2 x radix-3 for N1w = 6).
 
-template <class CFG>
+template <class CFG, class CX = typename CFG::cx_row>
 RD_HD void s_row_fwd(unsigned char* sm, int r) {
   const int khi = r % CFG::nb, c1 = r / CFG::nb;
   float4* Z = reinterpret_cast<float4*>(sm + CFG::offZ) + (size_t)khi * CFG::pitchZ + c1;
-  cf va[16], vb[16];
+  CX va[16], vb[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float4 p = Z[CFG::N1w * j];
-    va[j] = cf{p.x, p.y};
-    vb[j] = cf{p.z, p.w};
+    va[j] = cx_make<CX>(p.x, p.y);
+    vb[j] = cx_make<CX>(p.z, p.w);
   }
   fft16<-1>(va);
   fft16<-1>(vb);
@@ -425,14 +465,14 @@ RD_HD void s_row_fwd(unsigned char* sm, int r) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 w = tw[i];
-    cf a0 = va[pos16(2 * i)], b0 = vb[pos16(2 * i)];
+    CX a0 = va[pos16(2 * i)], b0 = vb[pos16(2 * i)];
     if (i > 0) {
       a0 = cmul(a0, cf{w.x, w.y});
       b0 = cmul(b0, cf{w.x, w.y});
     }
-    const cf a1 = cmul(va[pos16(2 * i + 1)], cf{w.z, w.w}), b1 = cmul(vb[pos16(2 * i + 1)], cf{w.z, w.w});
-    Z[CFG::N1w * (2 * i)] = make_float4(a0.re, a0.im, b0.re, b0.im);
-    Z[CFG::N1w * (2 * i + 1)] = make_float4(a1.re, a1.im, b1.re, b1.im);
+    const CX a1 = cmul(va[pos16(2 * i + 1)], cf{w.z, w.w}), b1 = cmul(vb[pos16(2 * i + 1)], cf{w.z, w.w});
+    Z[CFG::N1w * (2 * i)] = make_float4(cx_re(a0), cx_im(a0), cx_re(b0), cx_im(b0));
+    Z[CFG::N1w * (2 * i + 1)] = make_float4(cx_re(a1), cx_im(a1), cx_re(b1), cx_im(b1));
   }
 }
 
@@ -441,17 +481,19 @@ template <int N, int DIR>
 struct DftOut;
 template <int DIR>
 struct DftOut<4, DIR> {
-  static RD_HD cf run(const cf (&a)[4], int q) {
-    const cf t02p = a[0] + a[2], t02m = a[0] - a[2], t13p = a[1] + a[3], t13m = a[1] - a[3];
-    const cf jt = (DIR < 0) ? cf{t13m.im, -t13m.re} : cf{-t13m.im, t13m.re};  // (DIR i) * t13m
-    const cf e = (q & 1) ? t02m : t02p, o = (q & 1) ? jt : t13p;
+  template <class CX>
+  static RD_HD CX run(const CX (&a)[4], int q) {
+    const CX t02p = a[0] + a[2], t02m = a[0] - a[2], t13p = a[1] + a[3], t13m = a[1] - a[3];
+    const CX jt = cx_rot<DIR>(t13m);  // (DIR i) * t13m
+    const CX e = (q & 1) ? t02m : t02p, o = (q & 1) ? jt : t13p;
     return (q & 2) ? e - o : e + o;
   }
 };
 template <int DIR>
 struct DftOut<6, DIR> {
-  static RD_HD cf run(const cf (&a)[6], int q) {
-    cf e[3];
+  template <class CX>
+  static RD_HD CX run(const CX (&a)[6], int q) {
+    CX e[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) e[c] = (q & 1) ? a[c] - a[c + 3] : a[c] + a[c + 3];   // W_6^(3q) = (-1)^q
     // remaining: sum_c e[c] W_6^(c q); for odd q the factor W_6^(c q) = W_3^(c q') * (W_6^c)^(odd)...
@@ -461,18 +503,18 @@ struct DftOut<6, DIR> {
       e[2] = twidN<6, 2, DIR>(e[2]);
     }
     const int r3 = (q >> 1) % 3;
-    const cf s = e[1] + e[2], d = e[1] - e[2];
+    const CX s = e[1] + e[2], d = e[1] - e[2];
     if (r3 == 0) return e[0] + s;
     constexpr float kS = 0.86602540378443864676f;  // sin(2 pi / 3)
-    const cf m{e[0].re - 0.5f * s.re, e[0].im - 0.5f * s.im};
+    const CX m = cx_fma_s(s, -0.5f, e[0]);
     // W_3^(DIR) = -1/2 + DIR i kS ; r3 = 1: e0 + W e1 + W^2 e2 = m + (DIR i kS) d ; r3 = 2: m - (DIR i kS) d
     const float sg = ((r3 == 1) == (DIR > 0)) ? kS : -kS;
-    return cf{m.re - sg * d.im, m.im + sg * d.re};
+    return cx_fma_s(cx_rot<1>(d), sg, m);     // (m.re - sg d.im, m.im + sg d.re)
   }
 };
 
 // F[kh, kw] for kw >= 0 from the row-transformed, twiddled band buffer
-template <class CFG>
+template <class CFG, class CX = typename CFG::cx_band>
 RD_HD cf s_band_spectrum(const unsigned char* sm, int kh, int kw) {
   const float4* Z = reinterpret_cast<const float4*>(sm + CFG::offZ);
   const float* tab = reinterpret_cast<const float*>(sm + CFG::offTab);
@@ -480,17 +522,18 @@ RD_HD cf s_band_spectrum(const unsigned char* sm, int kh, int kw) {
   const int k2m = (16 - k2p) & 15, qm = (((-kw - k2m) / 16) % CFG::N1w + CFG::N1w) % CFG::N1w;
   const float4* zp = Z + (size_t)(kh + CFG::b) * CFG::pitchZ + CFG::N1w * k2p;
   const float4* zm = Z + (size_t)(CFG::b - kh) * CFG::pitchZ + CFG::N1w * k2m;
-  cf pa[CFG::N1w], pb[CFG::N1w], ma[CFG::N1w], mb[CFG::N1w];
+  CX pa[CFG::N1w], pb[CFG::N1w], ma[CFG::N1w], mb[CFG::N1w];
 #pragma unroll
   for (int c1 = 0; c1 < CFG::N1w; ++c1) {
     const float4 p = zp[c1], q = zm[c1];
-    pa[c1] = cf{p.x, p.y};
-    pb[c1] = cf{p.z, p.w};
-    ma[c1] = cf{q.x, q.y};
-    mb[c1] = cf{q.z, q.w};
+    pa[c1] = cx_make<CX>(p.x, p.y);
+    pb[c1] = cx_make<CX>(p.z, p.w);
+    ma[c1] = cx_make<CX>(q.x, q.y);
+    mb[c1] = cx_make<CX>(q.z, q.w);
   }
-  const cf upa = DftOut<CFG::N1w, -1>::run(pa, qp), upb = DftOut<CFG::N1w, -1>::run(pb, qp);
-  const cf uma = DftOut<CFG::N1w, -1>::run(ma, qm), umb = DftOut<CFG::N1w, -1>::run(mb, qm);
+  const CX Upa = DftOut<CFG::N1w, -1>::run(pa, qp), Upb = DftOut<CFG::N1w, -1>::run(pb, qp);
+  const CX Uma = DftOut<CFG::N1w, -1>::run(ma, qm), Umb = DftOut<CFG::N1w, -1>::run(mb, qm);
+  const cf upa{cx_re(Upa), cx_im(Upa)}, upb{cx_re(Upb), cx_im(Upb)}, uma{cx_re(Uma), cx_im(Uma)}, umb{cx_re(Umb), cx_im(Umb)};
   const cf g0{0.5f * (upa.re + uma.re), 0.5f * (upa.im - uma.im)};
   const cf g2{0.5f * (upa.im + uma.im), -0.5f * (upa.re - uma.re)};
   const cf g1{0.5f * (upb.re + umb.re), 0.5f * (upb.im - umb.im)};
@@ -544,7 +587,7 @@ RD_HD void s_band_amp(const unsigned char* sm, float* patch, int q) {
 }
 
 // inverse rows (direct band sums into the 16 radix-16 inputs, then radix-16 inverse), lanes <-> kh
-template <class CFG>
+template <class CFG, class CX = typename CFG::cx_row>
 RD_HD void s_row_inv(unsigned char* sm, int r) {
   const int khi = r % CFG::nb, c1 = r / CFG::nb;
   const float2* D = reinterpret_cast<const float2*>(sm + CFG::offD);
@@ -552,17 +595,17 @@ RD_HD void s_row_inv(unsigned char* sm, int r) {
   const float2* Dm = D + (size_t)(CFG::nb - 1 - khi) * CFG::dPitch;
   const float4* PT = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tPT) +
                      (size_t)c1 * CFG::nb + CFG::b;
-  cf va[16], vb[16];
+  CX va[16], vb[16];
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) {
-    cf aa{0, 0}, ab{0, 0};
+    CX aa = cx_make<CX>(0.f, 0.f), ab = cx_make<CX>(0.f, 0.f);
 #pragma unroll
     for (int mi = -CFG::MM; mi < CFG::MM; ++mi) {
       const int kw = k2 + 16 * mi;               // compile-time after unrolling
       if (kw >= -CFG::b && kw <= CFG::b) {
-        cf d;
-        if (kw >= 0) { const float2 t = Dp[kw]; d = cf{t.x, t.y}; }
-        else { const float2 t = Dm[-kw]; d = cf{t.x, -t.y}; }
+        CX d;
+        if (kw >= 0) { const float2 t = Dp[kw]; d = cx_make<CX>(t.x, t.y); }
+        else { const float2 t = Dm[-kw]; d = cx_make<CX>(t.x, -t.y); }
         const float4 p = PT[kw];
         cmac(aa, d, cf{p.x, p.y});
         cmac(ab, d, cf{p.z, p.w});
@@ -576,8 +619,8 @@ RD_HD void s_row_inv(unsigned char* sm, int r) {
   float4* Z = reinterpret_cast<float4*>(sm + CFG::offZ) + (size_t)khi * CFG::pitchZ + c1;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const cf a = va[pos16(j)], bq = vb[pos16(j)];
-    Z[CFG::N1w * j] = make_float4(a.re, a.im, bq.re, bq.im);
+    const CX a = va[pos16(j)], bq = vb[pos16(j)];
+    Z[CFG::N1w * j] = make_float4(cx_re(a), cx_im(a), cx_re(bq), cx_im(bq));
   }
 }
 

@@ -39,6 +39,16 @@ RD_HD void cmacc(cf& acc, cf a, cf w) {
   acc.im = fmaf(-a.re, w.im, acc.im);
 }
 
+// Generic accessors shared by the scalar (cf) and the register-pair (cp, ram_math_x2.cuh) complex types, so that a
+// phase body can be instantiated with either.
+template <class CX> struct CxMake;
+template <> struct CxMake<cf> { static RD_HD cf make(float re, float im) { return cf{re, im}; } };
+template <class CX> RD_HD CX cx_make(float re, float im) { return CxMake<CX>::make(re, im); }
+RD_HD float cx_re(cf a) { return a.re; }
+RD_HD float cx_im(cf a) { return a.im; }
+template <int DIR> RD_HD cf cx_rot(cf b) { return (DIR < 0) ? cf{b.im, -b.re} : cf{-b.im, b.re}; }   // (DIR i) * b
+RD_HD cf cx_fma_s(cf a, float s, cf c) { return cf{c.re + s * a.re, c.im + s * a.im}; }               // a * s + c
+
 // 4-point DFT in place. DIR = -1: forward kernel exp(-2 pi i nk/4); DIR = +1: inverse (unnormalised).
 template <int DIR>
 RD_HD void fft4(cf& a0, cf& a1, cf& a2, cf& a3) {

@@ -159,7 +159,7 @@ __device__ __forceinline__ void mp_task_c(unsigned char* sm, const float* __rest
   auto st = [&](size_t off, float4 v) { mp_stg_policy(y4 + off, v, pol_stream); };
   const int h1 = tid >> 4, c4 = strip * 16 + (tid & 15);
   for (int p = 0; p < CFG::HP; ++p) {
-    cf eva[8], evb[8], oda[8], odb[8];
+    cp eva[8], evb[8], oda[8], odb[8];
     m_inv_pruned<CFG>(sm, p, 0, tid);
     __syncthreads();
     s_inv_fft8<CFG>(sm, tid, 0, eva, evb);

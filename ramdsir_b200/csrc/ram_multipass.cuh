@@ -67,11 +67,13 @@ struct FftN;
 template <int DIR>
 struct FftN<16, DIR> {
   static RD_HD void run(cf (&v)[16]) { fft16<DIR>(v); }
+  static RD_HD void run(cp (&v)[16]) { fft16<DIR>(v); }
   static RD_HD constexpr int pos(int k) { return pos16(k); }
 };
 template <int DIR>
 struct FftN<8, DIR> {
   static RD_HD void run(cf (&v)[8]) { fft8<DIR>(v); }
+  static RD_HD void run(cp (&v)[8]) { fft8<DIR>(v); }
   static RD_HD constexpr int pos(int k) { return pos8(k); }
 };
 
@@ -112,49 +114,49 @@ RD_HD void m_f1_load_fft_tw_x2(LoadF4 ld, const unsigned char* sm, int strip, in
 
 template <class CFG, int K1>
 struct MF1Out {   // Zs[kh] (+)= TWP[p][kh] * sum_a W_16^(a k1) y[a][k1 mod 4]
-  static RD_HD void run(const cf (&y)[4][4], float2* zcol, const float2* twp, int k2, bool first) {
+  static RD_HD void run(const cp (&y)[4][4], float2* zcol, const float2* twp, int k2, bool first) {
     const int kh = k2 + 16 * K1;
     if (kh >= -CFG::b && kh <= CFG::b) {
-      cf o = SumA<CFG, K1, -1, 3>::run(y);
+      cp o = SumA<CFG, K1, -1, 3>::run(y);
       const float2 w = twp[kh];
       o = cmul(o, cf{w.x, w.y});
       float2* z = zcol + (size_t)(kh + CFG::b) * CFG::pitchZ * 2;
       if (!first) {
         const float2 old = *z;
-        o = cf{o.re + old.x, o.im + old.y};
+        o = o + cp_make(old.x, old.y);
       }
-      *z = make_float2(o.re, o.im);
+      *z = make_float2(cp_re(o), cp_im(o));
     }
     MF1Out<CFG, K1 + 1>::run(y, zcol, twp, k2, first);
   }
 };
 template <class CFG>
 struct MF1Out<CFG, CFG::MM> {
-  static RD_HD void run(const cf (&)[4][4], float2*, const float2*, int, bool) {}
+  static RD_HD void run(const cp (&)[4][4], float2*, const float2*, int, bool) {}
 };
 
 // Emit the band rows kh = k2 + 16 K1 from the finished 16-point transform X[k1 mod 16] (at v[pos16(.)]).
 template <class CFG, int K1>
 struct MF1OutFull {
-  static RD_HD void run(const cf (&v)[16], float2* zcol, const float2* twp, int k2, bool first) {
+  static RD_HD void run(const cp (&v)[16], float2* zcol, const float2* twp, int k2, bool first) {
     const int kh = k2 + 16 * K1;
     if (kh >= -CFG::b && kh <= CFG::b) {
-      cf o = v[pos16((K1 + 16) & 15)];
+      cp o = v[pos16((K1 + 16) & 15)];
       const float2 w = twp[kh];
       o = cmul(o, cf{w.x, w.y});
       float2* z = zcol + (size_t)(kh + CFG::b) * CFG::pitchZ * 2;
       if (!first) {
         const float2 old = *z;
-        o = cf{o.re + old.x, o.im + old.y};
+        o = o + cp_make(old.x, old.y);
       }
-      *z = make_float2(o.re, o.im);
+      *z = make_float2(cp_re(o), cp_im(o));
     }
     MF1OutFull<CFG, K1 + 1>::run(v, zcol, twp, k2, first);
   }
 };
 template <class CFG>
 struct MF1OutFull<CFG, CFG::MM> {
-  static RD_HD void run(const cf (&)[16], float2*, const float2*, int, bool) {}
+  static RD_HD void run(const cp (&)[16], float2*, const float2*, int, bool) {}
 };
 
 // Second stage of the 256-row sub-transform.  With a wide band (1024^2: 13 of the 16 residues k1 of every k2 are in
@@ -168,22 +170,22 @@ RD_HD void m_f1_pruned(unsigned char* sm, int p, int half, int u) {
   const float2* twp = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWP) +
                       p * CFG::nb + CFG::b;
   if constexpr (CFG::MM >= 6) {
-    cf v[16];
+    cp v[16];
 #pragma unroll
     for (int h1 = 0; h1 < 16; ++h1) {
       const float2 t = e[h1 * 32];
-      v[h1] = cf{t.x, t.y};
+      v[h1] = cp_make(t.x, t.y);
     }
     fft16<-1>(v);
     MF1OutFull<CFG, -CFG::MM>::run(v, zcol, twp, k2, p == 0);
   } else {
-    cf y[4][4];
+    cp y[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
 #pragma unroll
       for (int bq = 0; bq < 4; ++bq) {
         const float2 v = e[(a + 4 * bq) * 32];
-        y[a][bq] = cf{v.x, v.y};
+        y[a][bq] = cp_make(v.x, v.y);
       }
       fft4<-1>(y[a][0], y[a][1], y[a][2], y[a][3]);
     }
@@ -198,30 +200,30 @@ RD_HD void m_inv_pruned(unsigned char* sm, int p, int par, int u) {
   const float2* zcol = reinterpret_cast<const float2*>(sm + CFG::offZ) + c * 2 + col;
   const float2* twp = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWP) +
                       p * CFG::nb + CFG::b;
-  cf in[2 * CFG::MM];
+  cp in[2 * CFG::MM];
 #pragma unroll
   for (int i = 0; i < 2 * CFG::MM; ++i) {
     const int kh = k2 + 16 * (i - CFG::MM);
-    cf v{0.f, 0.f};
+    cp v = cp_make(0.f, 0.f);
     if (kh >= -CFG::b && kh <= CFG::b) {
       const float2 z = zcol[(size_t)(kh + CFG::b) * CFG::pitchZ * 2];
       const float2 w = twp[kh];
-      v = cmulc(cf{z.x, z.y}, cf{w.x, w.y});   // x W_H^(-p kh)
+      v = cmulc(cp_make(z.x, z.y), cf{w.x, w.y});   // x W_H^(-p kh)
     }
     in[i] = v;
   }
   float2* e = reinterpret_cast<float2*>(sm + CFG::offE) + ((size_t)k2l * 16 * 16 + c) * 2 + col;
   if constexpr (CFG::MM >= 6) {
     // wide band: a complete inverse 16-point FFT over the residues k1 (those outside [-MM, MM) are zero)
-    cf v[16];
+    cp v[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const int k1 = k < 8 ? k : k - 16;
-      v[k] = (k1 >= -CFG::MM && k1 < CFG::MM) ? in[k1 + CFG::MM] : cf{0.f, 0.f};
+      v[k] = (k1 >= -CFG::MM && k1 < CFG::MM) ? in[k1 + CFG::MM] : cp_make(0.f, 0.f);
     }
     fft16<1>(v);
 #pragma unroll
-    for (int h1 = 0; h1 < 16; ++h1) e[h1 * 32] = make_float2(v[pos16(h1)].re, v[pos16(h1)].im);
+    for (int h1 = 0; h1 < 16; ++h1) e[h1 * 32] = make_float2(cp_re(v[pos16(h1)]), cp_im(v[pos16(h1)]));
   } else {
     InvA<CFG, 0>::run(in, e);
   }
@@ -230,16 +232,16 @@ RD_HD void m_inv_pruned(unsigned char* sm, int p, int par, int u) {
 template <class CFG, int J>
 struct MCombine {
   template <class LoadF4, class StoreF4, class EPI>
-  static RD_HD void run(LoadF4 ld, StoreF4 st, EPI ep, int h1, int p, int c4, const cf (&eva)[8], const cf (&evb)[8],
-                        const cf (&oda)[8], const cf (&odb)[8]) {
-    const cf wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
-    const cf ea = eva[pos8(J)], eb = evb[pos8(J)];
+  static RD_HD void run(LoadF4 ld, StoreF4 st, EPI ep, int h1, int p, int c4, const cp (&eva)[8], const cp (&evb)[8],
+                        const cp (&oda)[8], const cp (&odb)[8]) {
+    const cp wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
+    const cp ea = eva[pos8(J)], eb = evb[pos8(J)];
 #pragma unroll
     for (int hi = 0; hi < 2; ++hi) {
       const size_t off = (size_t)((h1 + 16 * (J + 8 * hi)) * CFG::HP + p) * CFG::M + c4;
-      const cf a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
+      const cp a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
       const float4 x = ld(off);
-      st(off, make_float4(ep(x.x, a.re), ep(x.y, bq.re), ep(x.z, a.im), ep(x.w, bq.im)));
+      st(off, make_float4(ep(x.x, cp_re(a)), ep(x.y, cp_re(bq)), ep(x.z, cp_im(a)), ep(x.w, cp_im(bq))));
     }
     MCombine<CFG, J + 1>::run(ld, st, ep, h1, p, c4, eva, evb, oda, odb);
   }
@@ -247,7 +249,7 @@ struct MCombine {
 template <class CFG>
 struct MCombine<CFG, 8> {
   template <class LoadF4, class StoreF4, class EPI>
-  static RD_HD void run(LoadF4, StoreF4, EPI, int, int, int, const cf (&)[8], const cf (&)[8], const cf (&)[8], const cf (&)[8]) {}
+  static RD_HD void run(LoadF4, StoreF4, EPI, int, int, int, const cp (&)[8], const cp (&)[8], const cp (&)[8], const cp (&)[8]) {}
 };
 
 // ===== pass B ==================================================================================
@@ -257,12 +259,12 @@ RD_HD void m_row_stage1(float4* Rbase, const float* tab, int task) {
   const int row = task / CFG::N1w, c1 = task % CFG::N1w;
   float4* R = Rbase + (size_t)row * CFG::rowPitch + c1;
   const float2* tw = reinterpret_cast<const float2*>(tab + CFG::tTWM) + c1;   // TWM is stored [k2][c1]: lanes <-> c1 read contiguously
-  cf va[16], vb[16];
+  cp va[16], vb[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float4 q = R[CFG::SP * j];
-    va[j] = cf{q.x, q.y};
-    vb[j] = cf{q.z, q.w};
+    va[j] = cp_make(q.x, q.y);
+    vb[j] = cp_make(q.z, q.w);
     if (DIR > 0) {   // inverse: undo the twiddle first (input index is k2)
       const float2 w = tw[j * CFG::N1w];
       va[j] = cmulc(va[j], cf{w.x, w.y});
@@ -273,13 +275,13 @@ RD_HD void m_row_stage1(float4* Rbase, const float* tab, int task) {
   fft16<DIR>(vb);
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    cf a = va[pos16(k)], bq = vb[pos16(k)];
+    cp a = va[pos16(k)], bq = vb[pos16(k)];
     if (DIR < 0) {
       const float2 w = tw[k * CFG::N1w];
       a = cmul(a, cf{w.x, w.y});
       bq = cmul(bq, cf{w.x, w.y});
     }
-    R[CFG::SP * k] = make_float4(a.re, a.im, bq.re, bq.im);
+    R[CFG::SP * k] = make_float4(cp_re(a), cp_im(a), cp_re(bq), cp_im(bq));
   }
 }
 
@@ -288,19 +290,19 @@ template <class CFG, int DIR>
 RD_HD void m_row_stage2(float4* Rbase, int task) {
   const int row = task / 16, k2 = task % 16;
   float4* R = Rbase + (size_t)row * CFG::rowPitch + CFG::SP * k2;
-  cf va[CFG::N1w], vb[CFG::N1w];
+  cp va[CFG::N1w], vb[CFG::N1w];
 #pragma unroll
   for (int i = 0; i < CFG::N1w; ++i) {
     const float4 q = R[i];
-    va[i] = cf{q.x, q.y};
-    vb[i] = cf{q.z, q.w};
+    va[i] = cp_make(q.x, q.y);
+    vb[i] = cp_make(q.z, q.w);
   }
   FftN<CFG::N1w, DIR>::run(va);
   FftN<CFG::N1w, DIR>::run(vb);
 #pragma unroll
   for (int i = 0; i < CFG::N1w; ++i) {
-    const cf a = va[FftN<CFG::N1w, DIR>::pos(i)], bq = vb[FftN<CFG::N1w, DIR>::pos(i)];
-    R[i] = make_float4(a.re, a.im, bq.re, bq.im);
+    const cp a = va[FftN<CFG::N1w, DIR>::pos(i)], bq = vb[FftN<CFG::N1w, DIR>::pos(i)];
+    R[i] = make_float4(cp_re(a), cp_im(a), cp_re(bq), cp_im(bq));
   }
 }
 

@@ -18,7 +18,8 @@ static void run_plane(const FusedShape& S, unsigned char* sm, const float* x, co
   auto ld = [&](size_t off) { const float* p = x + 4 * off; return make_float4(p[0], p[1], p[2], p[3]); };
   auto st = [&](size_t off, float4 v) { float* p = y + 4 * off; p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; };
   const int NT = S.nthreads;
-  std::vector<cf> regs((size_t)NT * 32);
+  std::vector<cp> regs_store((size_t)NT * 32);   // 8-byte aligned storage, viewed as cf / cp / cf2 by the phases
+  cf* regs = reinterpret_cast<cf*>(regs_store.data());
   for (int strip = 0; strip < S.nstrips; ++strip) {
     for (int t = 0; t < NT; ++t) {
       cf(&va)[16] = *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]);
@@ -84,7 +85,8 @@ static void run_plane_static(unsigned char* sm, const float* x, const float* pat
   auto ld = [&](size_t off) { const float* p = x + 4 * off; return make_float4(p[0], p[1], p[2], p[3]); };
   auto st = [&](size_t off, float4 v, float4) { float* p = y + 4 * off; p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; };
   constexpr int NT = CFG::nthreads;
-  std::vector<cf> regs((size_t)NT * 32);
+  std::vector<cp> regs_store((size_t)NT * 32);   // 8-byte aligned storage, viewed as cf / cp / cf2 by the phases
+  cf* regs = reinterpret_cast<cf*>(regs_store.data());
   auto A = [&](int t) -> cf(&)[16] { return *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]); };
   auto Bv = [&](int t) -> cf(&)[16] { return *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32 + 16]); };
   for (int strip = 0; strip < CFG::nstrips; ++strip) {
@@ -109,15 +111,17 @@ static void run_plane_static(unsigned char* sm, const float* x, const float* pat
     for (int par = 0; par < 2; ++par) {
       for (int u = 0; u < 256; ++u) s_inv_pruned<CFG>(sm, strip, par, u);
       for (int t = 0; t < NT; ++t) {
-        cf(&pa)[8] = *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 32 + 16 * par]);
-        cf(&pb)[8] = *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 32 + 16 * par + 8]);
+        using CX = typename CFG::cx_fft8;
+        CX(&pa)[8] = *reinterpret_cast<CX(*)[8]>(&regs[(size_t)t * 32 + 16 * par]);
+        CX(&pb)[8] = *reinterpret_cast<CX(*)[8]>(&regs[(size_t)t * 32 + 16 * par + 8]);
         s_inv_fft8<CFG>(sm, t, par, pa, pb);
       }
     }
     for (int t = 0; t < NT; ++t) {
       cf* r = &regs[(size_t)t * 32];
-      s_inv_combine_store<CFG>(ld, st, ep, strip, t, *reinterpret_cast<cf(*)[8]>(r), *reinterpret_cast<cf(*)[8]>(r + 8),
-                               *reinterpret_cast<cf(*)[8]>(r + 16), *reinterpret_cast<cf(*)[8]>(r + 24));
+      using CX = typename CFG::cx_fft8;
+      s_inv_combine_store<CFG>(ld, st, ep, strip, t, *reinterpret_cast<CX(*)[8]>(r), *reinterpret_cast<CX(*)[8]>(r + 8),
+                               *reinterpret_cast<CX(*)[8]>(r + 16), *reinterpret_cast<CX(*)[8]>(r + 24));
     }
   }
 }
@@ -171,7 +175,8 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
   multipass_tables_b<CFG>(reinterpret_cast<float*>(smb.data() + CFG::bOffTab));
   const size_t plane_px = (size_t)CFG::H * CFG::W, psz = (size_t)CFG::nb * CFG::nb;
   std::vector<float4> Zg((size_t)CFG::nb * CFG::M);
-  std::vector<cf> regs((size_t)256 * 32);
+  std::vector<cp> regs_store((size_t)256 * 32);
+  cf* regs = reinterpret_cast<cf*>(regs_store.data());
   for (int i = 0; i < B; ++i)
     for (int c = 0; c < C; ++c) {
       const size_t pl = (size_t)i * C + c;
@@ -238,13 +243,13 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
           for (int par = 0; par < 2; ++par) {
             for (int u = 0; u < 256; ++u) m_inv_pruned<CFG>(sm.data(), p, par, u);
             for (int t = 0; t < 256; ++t)
-              s_inv_fft8<CFG>(sm.data(), t, par, *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 32 + 16 * par]),
-                              *reinterpret_cast<cf(*)[8]>(&regs[(size_t)t * 32 + 16 * par + 8]));
+              s_inv_fft8<CFG>(sm.data(), t, par, *reinterpret_cast<cp(*)[8]>(&regs[(size_t)t * 32 + 16 * par]),
+                              *reinterpret_cast<cp(*)[8]>(&regs[(size_t)t * 32 + 16 * par + 8]));
           }
           for (int t = 0; t < 256; ++t) {
             cf* r = &regs[(size_t)t * 32];
-            MCombine<CFG, 0>::run(ld, st, EpiClamp{ep.lo, ep.hi, ep.scale, ep.shift}, t >> 4, p, strip * 16 + (t & 15), *reinterpret_cast<cf(*)[8]>(r),
-                                  *reinterpret_cast<cf(*)[8]>(r + 8), *reinterpret_cast<cf(*)[8]>(r + 16), *reinterpret_cast<cf(*)[8]>(r + 24));
+            MCombine<CFG, 0>::run(ld, st, EpiClamp{ep.lo, ep.hi, ep.scale, ep.shift}, t >> 4, p, strip * 16 + (t & 15), *reinterpret_cast<cp(*)[8]>(r),
+                                  *reinterpret_cast<cp(*)[8]>(r + 8), *reinterpret_cast<cp(*)[8]>(r + 16), *reinterpret_cast<cp(*)[8]>(r + 24));
           }
         }
       }
