@@ -100,34 +100,9 @@ struct SCfg {
   static_assert(nthreads >= 256 && nthreads <= 512, "block size out of range");
 };
 
-// ---- F1a: load 16 strided rows, radix-16 over j, multiply by TWH[h1][k2] = W_H^(h1 k2) --------------
-template <class CFG, class LoadF4>
-RD_HD void s_f1_load_fft_tw(LoadF4 ld, const unsigned char* sm, int strip, int t, cf (&va)[16], cf (&vb)[16]) {
-  const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float4 p = ld((size_t)(h1 + CFG::N1h * j) * CFG::M + c4);
-    va[j] = cf{p.x, p.z};
-    vb[j] = cf{p.y, p.w};
-  }
-  fft16<-1>(va);
-  fft16<-1>(vb);
-  const float4* tw = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWH) +
-                     h1 * (CFG::twhPitch / 2);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 w = tw[i];
-    if (i > 0) {
-      va[pos16(2 * i)] = cmul(va[pos16(2 * i)], cf{w.x, w.y});
-      vb[pos16(2 * i)] = cmul(vb[pos16(2 * i)], cf{w.x, w.y});
-    }
-    va[pos16(2 * i + 1)] = cmul(va[pos16(2 * i + 1)], cf{w.z, w.w});
-    vb[pos16(2 * i + 1)] = cmul(vb[pos16(2 * i + 1)], cf{w.z, w.w});
-  }
-}
-
-// Half-ahead variant of F1a: rows j = 0..7 of a strip are loaded one stage early (s_f1_load_rows<0>), rows
-// j = 8..15 at the start of the strip (s_f1_load_rows<8>); s_f1_fft_tw_raw then transforms and twiddles.
+// ---- F1a: load 16 strided rows (h1 + N1h j), radix-16 over j, multiply by TWH[h1][k2] = W_H^(h1 k2) ------------
+// Half-ahead form: rows j = 0..7 of a strip can be requested one stage early (s_f1_load_rows<0>), rows j = 8..15 at the
+// start of the strip (s_f1_load_rows<8>); s_f1_fft_tw_raw_x2 then transforms and twiddles.
 template <class CFG, int JBASE, class LoadF4>
 RD_HD void s_f1_load_rows(LoadF4 ld, int strip, int t, float4 (&raw)[8]) {
   const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
@@ -135,38 +110,10 @@ RD_HD void s_f1_load_rows(LoadF4 ld, int strip, int t, float4 (&raw)[8]) {
   for (int j = 0; j < 8; ++j) raw[j] = ld((size_t)(h1 + CFG::N1h * (JBASE + j)) * CFG::M + c4);
 }
 
-template <class CFG>
-RD_HD void s_f1_fft_tw_raw(const unsigned char* sm, int t, const float4 (&lo)[8], const float4 (&hi)[8], cf (&va)[16], cf (&vb)[16]) {
-  const int h1 = t >> 4;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    va[j] = cf{lo[j].x, lo[j].z};
-    vb[j] = cf{lo[j].y, lo[j].w};
-    va[j + 8] = cf{hi[j].x, hi[j].z};
-    vb[j + 8] = cf{hi[j].y, hi[j].w};
-  }
-  fft16<-1>(va);
-  fft16<-1>(vb);
-  const float4* tw = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWH) +
-                     h1 * (CFG::twhPitch / 2);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 w = tw[i];
-    if (i > 0) {
-      va[pos16(2 * i)] = cmul(va[pos16(2 * i)], cf{w.x, w.y});
-      vb[pos16(2 * i)] = cmul(vb[pos16(2 * i)], cf{w.x, w.y});
-    }
-    va[pos16(2 * i + 1)] = cmul(va[pos16(2 * i + 1)], cf{w.z, w.w});
-    vb[pos16(2 * i + 1)] = cmul(vb[pos16(2 * i + 1)], cf{w.z, w.w});
-  }
-}
-
-// ---- packed-pair (FADD2 / FMUL2 / FFMA2) versions of F1a / F1b: the two packed columns of a thread travel as
-// register pairs through the radix-16 and the TWH twiddles at half the issue slots (this phase is issue-bound once its
-// loads have landed); E keeps its layout, at the price of two or three MOVs per published float4.  Measured on B200:
-// +1.2 % (256^2), +3.2 % (384^2).  The same treatment of the inverse second stage (+0.6 % / -7.5 %) and of the row
-// transforms (-1 % / -1.8 %) does not pay: those phases wait on shared memory and barriers, not on issue slots, and
-// the pair <-> (re, im) permutes around their LDS / STS cost more than the arithmetic they save.
+// ---- F1a / F1b on column pairs (cf2, ram_math_x2.cuh): the two packed columns of a thread travel as register pairs
+// through the radix-16 and the TWH twiddles at half the issue slots -- this phase is issue-bound once its loads have
+// landed.  E keeps its (a.re, a.im, b.re, b.im) layout at the price of two or three MOVs per published float4.
+// Measured on B200: +1.2 % (256^2), +3.2 % (384^2) of kernel time.
 template <class CFG>
 RD_HD void s_f1_fft_tw_x2(const unsigned char* sm, int t, cf2 (&v)[16]) {
   const int h1 = t >> 4;
@@ -203,18 +150,6 @@ RD_HD void s_f1_store_half_x2(unsigned char* sm, int t, int half, const cf2 (&v)
   for (int k2l = 0; k2l < 8; ++k2l) {
     const cf2 a = half ? v[pos16(8 + k2l)] : v[pos16(k2l)];
     E[k2l * CFG::N1h * 16] = make_float4(f2_lo(a.re), f2_lo(a.im), f2_hi(a.re), f2_hi(a.im));
-  }
-}
-
-// ---- F1b: publish k2 in [8 half, 8 half + 8) to E[k2l][h1][c] ---------------------------------------
-template <class CFG>
-RD_HD void s_f1_store_half(unsigned char* sm, int t, int half, const cf (&va)[16], const cf (&vb)[16]) {
-  float4* E = reinterpret_cast<float4*>(sm + CFG::offE) + (t >> 4) * 16 + (t & 15);
-#pragma unroll
-  for (int k2l = 0; k2l < 8; ++k2l) {
-    const cf a = half ? va[pos16(8 + k2l)] : va[pos16(k2l)];
-    const cf bq = half ? vb[pos16(8 + k2l)] : vb[pos16(k2l)];
-    E[k2l * CFG::N1h * 16] = make_float4(a.re, a.im, bq.re, bq.im);
   }
 }
 

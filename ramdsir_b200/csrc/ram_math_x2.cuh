@@ -45,8 +45,6 @@ RD_HD cf2 operator+(cf2 a, cf2 b) { return cf2{a.re + b.re, a.im + b.im}; }
 RD_HD cf2 operator-(cf2 a, cf2 b) { return cf2{a.re - b.re, a.im - b.im}; }
 // a * w, w given as packed (broadcast) twiddle
 RD_HD cf2 cmul2(cf2 a, f2 wr, f2 wi) { return cf2{xfma(a.re, wr, f2_neg(a.im * wi)), xfma(a.re, wi, a.im * wr)}; }
-// a * conj(w)
-RD_HD cf2 cmulc2(cf2 a, f2 wr, f2 wi) { return cf2{xfma(a.re, wr, a.im * wi), xfma(a.im, wr, f2_neg(a.re * wi))}; }
 // memory layout of a cf2: float4 (re.a, re.b, im.a, im.b)  ("RRII")
 RD_HD cf2 cf2_from(float4 q) { return cf2{f2_make(q.x, q.y), f2_make(q.z, q.w)}; }
 RD_HD float4 cf2_to(cf2 a) { return make_float4(f2_lo(a.re), f2_hi(a.re), f2_lo(a.im), f2_hi(a.im)); }
@@ -94,21 +92,6 @@ RD_HD void fft16x(cf2 (&v)[16]) {
   v[3 + 4 * 3] = twidNx<16, 9, DIR>(v[3 + 4 * 3]);
 #pragma unroll
   for (int k2 = 0; k2 < 4; ++k2) fft4x<DIR>(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
-}
-
-template <int DIR>
-RD_HD void fft8x(cf2 (&v)[8]) {
-#pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    const cf2 a = v[n] + v[n + 4], d = v[n] - v[n + 4];
-    v[n] = a;
-    v[n + 4] = d;
-  }
-  v[5] = twidNx<8, 1, DIR>(v[5]);
-  v[6] = twidNx<8, 2, DIR>(v[6]);
-  v[7] = twidNx<8, 3, DIR>(v[7]);
-  fft4x<DIR>(v[0], v[1], v[2], v[3]);
-  fft4x<DIR>(v[4], v[5], v[6], v[7]);
 }
 
 // =================================================================================================================

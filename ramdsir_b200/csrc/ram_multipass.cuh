@@ -78,32 +78,7 @@ struct FftN<8, DIR> {
 };
 
 // ===== pass A ==================================================================================
-template <class CFG, class LoadF4>
-RD_HD void m_f1_load_fft_tw(LoadF4 ld, const unsigned char* sm, int strip, int p, int t, cf (&va)[16], cf (&vb)[16]) {
-  const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float4 q = ld((size_t)((h1 + 16 * j) * CFG::HP + p) * CFG::M + c4);
-    va[j] = cf{q.x, q.z};
-    vb[j] = cf{q.y, q.w};
-  }
-  fft16<-1>(va);
-  fft16<-1>(vb);
-  const float4* tw = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + CFG::offTab) + CFG::tTWH) +
-                     h1 * (CFG::twhPitch / 2);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 w = tw[i];
-    if (i > 0) {
-      va[pos16(2 * i)] = cmul(va[pos16(2 * i)], cf{w.x, w.y});
-      vb[pos16(2 * i)] = cmul(vb[pos16(2 * i)], cf{w.x, w.y});
-    }
-    va[pos16(2 * i + 1)] = cmul(va[pos16(2 * i + 1)], cf{w.z, w.w});
-    vb[pos16(2 * i + 1)] = cmul(vb[pos16(2 * i + 1)], cf{w.z, w.w});
-  }
-}
-
-// packed-pair version (see s_f1_fft_tw_x2): the radix-16 and the TWH twiddles on register pairs
+// F1a of a polyphase sub-column on packed pairs (see s_f1_fft_tw_x2): rows (h1 + 16 j) HP + p
 template <class CFG, class LoadF4>
 RD_HD void m_f1_load_fft_tw_x2(LoadF4 ld, const unsigned char* sm, int strip, int p, int t, cf2 (&v)[16]) {
   const int h1 = t >> 4, c4 = strip * 16 + (t & 15);

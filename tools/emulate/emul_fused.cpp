@@ -186,12 +186,10 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
       for (int strip = 0; strip < CFG::nstrips; ++strip) {
         for (int p = 0; p < CFG::HP; ++p) {
           for (int t = 0; t < 256; ++t)
-            m_f1_load_fft_tw<CFG>(ld, sm.data(), strip, p, t, *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]),
-                                  *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32 + 16]));
+            m_f1_load_fft_tw_x2<CFG>(ld, sm.data(), strip, p, t, *reinterpret_cast<cf2(*)[16]>(&regs[(size_t)t * 32]));
           for (int half = 0; half < 2; ++half) {
             for (int t = 0; t < 256; ++t)
-              s_f1_store_half<CFG>(sm.data(), t, half, *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32]),
-                                   *reinterpret_cast<cf(*)[16]>(&regs[(size_t)t * 32 + 16]));
+              s_f1_store_half_x2<CFG>(sm.data(), t, half, *reinterpret_cast<cf2(*)[16]>(&regs[(size_t)t * 32]));
             for (int u = 0; u < 256; ++u) m_f1_pruned<CFG>(sm.data(), p, half, u);
           }
         }
