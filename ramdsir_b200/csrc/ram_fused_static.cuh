@@ -424,6 +424,28 @@ struct DftOut<4, DIR> {
     return (q & 2) ? e - o : e + o;
   }
 };
+// The same output with the dependence on q moved into three per-task factors: X[q] = (a0 + s2 a2) + (c -+ i s)(a1 + s2 a3),
+// s2 = (-1)^q, (c, s) = (cos, sin)(pi q / 2) -- eight FFMA and no selects per vector (the band task evaluates four
+// vectors with two values of q).  The factors are 0 and +-1, so every product is exact and a constant row still gives
+// exact zeros off q = 0.
+struct Rot4 {
+  float s2, c, s;
+};
+RD_HD Rot4 rot4_of(int q) {
+  Rot4 r;
+  const float sgn = (q & 2) ? -1.f : 1.f;
+  r.s2 = (q & 1) ? -1.f : 1.f;
+  r.c = (q & 1) ? 0.f : sgn;
+  r.s = (q & 1) ? sgn : 0.f;
+  return r;
+}
+template <int DIR>
+RD_HD cf dft4_out(const cf (&a)[4], Rot4 r) {
+  const cf t1{fmaf(r.s2, a[2].re, a[0].re), fmaf(r.s2, a[2].im, a[0].im)};
+  const cf t2{fmaf(r.s2, a[3].re, a[1].re), fmaf(r.s2, a[3].im, a[1].im)};
+  const float sg = (DIR < 0) ? r.s : -r.s;     // forward: (c - i s) t2;  inverse: (c + i s) t2
+  return cf{fmaf(sg, t2.im, fmaf(r.c, t2.re, t1.re)), fmaf(-sg, t2.re, fmaf(r.c, t2.im, t1.im))};
+}
 template <int DIR>
 struct DftOut<6, DIR> {
   template <class CX>
@@ -466,9 +488,21 @@ RD_HD cf s_band_spectrum(const unsigned char* sm, int kh, int kw) {
     ma[c1] = cx_make<CX>(q.x, q.y);
     mb[c1] = cx_make<CX>(q.z, q.w);
   }
-  const CX Upa = DftOut<CFG::N1w, -1>::run(pa, qp), Upb = DftOut<CFG::N1w, -1>::run(pb, qp);
-  const CX Uma = DftOut<CFG::N1w, -1>::run(ma, qm), Umb = DftOut<CFG::N1w, -1>::run(mb, qm);
-  const cf upa{cx_re(Upa), cx_im(Upa)}, upb{cx_re(Upb), cx_im(Upb)}, uma{cx_re(Uma), cx_im(Uma)}, umb{cx_re(Umb), cx_im(Umb)};
+  cf upa, upb, uma, umb;
+  if constexpr (CFG::N1w == 4 && std::is_same<CX, cf>::value) {
+    const Rot4 rp = rot4_of(qp), rm = rot4_of(qm);
+    upa = dft4_out<-1>(pa, rp);
+    upb = dft4_out<-1>(pb, rp);
+    uma = dft4_out<-1>(ma, rm);
+    umb = dft4_out<-1>(mb, rm);
+  } else {
+    const CX Upa = DftOut<CFG::N1w, -1>::run(pa, qp), Upb = DftOut<CFG::N1w, -1>::run(pb, qp);
+    const CX Uma = DftOut<CFG::N1w, -1>::run(ma, qm), Umb = DftOut<CFG::N1w, -1>::run(mb, qm);
+    upa = cf{cx_re(Upa), cx_im(Upa)};
+    upb = cf{cx_re(Upb), cx_im(Upb)};
+    uma = cf{cx_re(Uma), cx_im(Uma)};
+    umb = cf{cx_re(Umb), cx_im(Umb)};
+  }
   const cf g0{0.5f * (upa.re + uma.re), 0.5f * (upa.im - uma.im)};
   const cf g2{0.5f * (upa.im + uma.im), -0.5f * (upa.re - uma.re)};
   const cf g1{0.5f * (upb.re + umb.re), 0.5f * (upb.im - umb.im)};
