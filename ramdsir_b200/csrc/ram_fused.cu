@@ -145,6 +145,38 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "}" :: "r"(bar), "r"(parity) : "memory");
 }
 
+// ---- tensor memory as a stash for x (no MMA involved) ---------------------------------------------------------------
+// TMEM is 128 lanes x 512 columns x 32 bit per SM; a warp reaches the 32 lanes of quadrant (warp % 4) and each thread
+// its own lane, so `tcgen05.st / ld .32x32b.xN` moves N registers of every thread to / from N columns of its lane: a
+// private, explicitly addressed scratch that never touches the LSU / L1TEX path.  With two CTAs per SM each CTA owns
+// 256 columns = 128 per thread (warps w and w + 4 share a quadrant) = the x quads of TWO of the plane's four strips:
+// the inverse pass takes those from TMEM instead of reading them a second time through L2.
+__device__ __forceinline__ void tmem_alloc(unsigned smem_slot, unsigned ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_slot), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// 8 quads (32 registers) -> 32 columns
+__device__ __forceinline__ void tmem_st_quads8(unsigned taddr, float4 q0, float4 q1, float4 q2, float4 q3, float4 q4, float4 q5,
+                                               float4 q6, float4 q7) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :: "r"(taddr), "f"(q0.x), "f"(q0.y), "f"(q0.z), "f"(q0.w), "f"(q1.x), "f"(q1.y), "f"(q1.z), "f"(q1.w), "f"(q2.x), "f"(q2.y),
+         "f"(q2.z), "f"(q2.w), "f"(q3.x), "f"(q3.y), "f"(q3.z), "f"(q3.w), "f"(q4.x), "f"(q4.y), "f"(q4.z), "f"(q4.w), "f"(q5.x),
+         "f"(q5.y), "f"(q5.z), "f"(q5.w), "f"(q6.x), "f"(q6.y), "f"(q6.z), "f"(q6.w), "f"(q7.x), "f"(q7.y), "f"(q7.z), "f"(q7.w)
+      : "memory");
+}
+// 2 quads (8 columns) -> registers; the caller waits with tmem_wait_ld() before using them
+__device__ __forceinline__ void tmem_ld_quads2(unsigned taddr, float4& a, float4& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Each thread prefetches 2 of the 128-byte lines its warp will load for column strip `strip`:
 // a warp covers rows (h1w + (lane >> 4)) + N1h * (lane & 15), 256 bytes (2 lines) each.
 template <class CFG>
@@ -178,6 +210,46 @@ struct MixScalars {
   float cscale, cshift;   // fused dual output: clean = x * cscale + cshift
 };
 
+// which static kernels stash x in tensor memory (-DRD_NO_TMEM_STASH: none, for A/B runs)
+template <class CFG, bool BANK, class TIn>
+struct StashX {
+#ifdef RD_NO_TMEM_STASH
+  static constexpr bool value = false;
+#else
+  static constexpr bool value = CFG::kTwoCtas && !BANK && std::is_same<TIn, float>::value;
+#endif
+};
+
+// Combine (ram_fused_static.cuh) with the x quads of rows J and J + 8 coming from the thread's TMEM columns
+// [8 J, 8 J + 8): the load of pair J + 1 is in flight while pair J is combined and stored.
+template <class CFG, int J>
+struct CombineT {
+  template <class StoreF4, class EPI, class CX>
+  static __device__ __forceinline__ void run(unsigned taddr, StoreF4 st, EPI ep, size_t base, float4 x0, float4 x1, const CX (&eva)[8],
+                                             const CX (&evb)[8], const CX (&oda)[8], const CX (&odb)[8]) {
+    tmem_wait_ld();                                   // pair J has landed in (x0, x1)
+    float4 n0 = x0, n1 = x1;
+    if (J < 7) tmem_ld_quads2(taddr + 8u * (J + 1), n0, n1);
+    const CX wa = twidN<16, J, 1>(oda[pos8(J)]), wb = twidN<16, J, 1>(odb[pos8(J)]);
+    const CX ea = eva[pos8(J)], eb = evb[pos8(J)];
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const size_t off = base + (size_t)(CFG::N1h * (J + 8 * hi)) * CFG::M;
+      const CX a = hi ? ea - wa : ea + wa, bq = hi ? eb - wb : eb + wb;
+      const float4 x = hi ? x1 : x0;
+      const float4 y = make_float4(ep(x.x, cx_re(a)), ep(x.y, cx_re(bq)), ep(x.z, cx_im(a)), ep(x.w, cx_im(bq)));
+      st(off, y, x);
+    }
+    CombineT<CFG, J + 1>::run(taddr, st, ep, base, n0, n1, eva, evb, oda, odb);
+  }
+};
+template <class CFG>
+struct CombineT<CFG, 8> {
+  template <class StoreF4, class EPI, class CX>
+  static __device__ __forceinline__ void run(unsigned, StoreF4, EPI, size_t, float4, float4, const CX (&)[8], const CX (&)[8],
+                                             const CX (&)[8], const CX (&)[8]) {}
+};
+
 template <class CFG, bool BANK, bool DUAL, class TIn, class EPI>
 __global__ void __launch_bounds__(CFG::nthreads, (CFG::smemBytes <= 113 * 1024) ? 2 : 1)
 ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ bank,
@@ -202,7 +274,20 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
     mbar_expect_tx(bar_tab, CFG::tabBytes);
     bulk_g2s(smem_u32(sm + CFG::offTab), tables, CFG::tabBytes, bar_tab);
   }
+  // x stash in tensor memory: two-CTAs-per-SM mix kernels with float32 sources (see tmem_* above)
+  constexpr bool kStash = StashX<CFG, BANK, TIn>::value;
+  constexpr int kStashStrips = 2;                            // strips 0 and 1: read first, re-read last
+  constexpr unsigned kTmemCols = 256;                        // half of the SM's tensor memory per CTA
+  if (kStash && tid < 32) tmem_alloc(smem_u32(sm + CFG::offBar + 16), kTmemCols);
+  if (kStash) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  unsigned tmem_mine = 0, tmem_base = 0;
+  if (kStash) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_base = *reinterpret_cast<const volatile unsigned*>(sm + CFG::offBar + 16);
+    // this thread's 128 columns: lane quadrant = warp % 4 (address bits 31:16 = lane), column half = warp / 4
+    tmem_mine = tmem_base + ((unsigned)((tid >> 5) & 3) << 21) + (unsigned)(tid >> 7) * 128u;
+  }
   mbar_wait(bar_tab, 0);
   unsigned patch_parity = 0;
   constexpr size_t plane_px = (size_t)CFG::H * CFG::W;
@@ -253,7 +338,24 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
     } else {
       for (int strip = 0; strip < CFG::nstrips; ++strip) {
         cf2 v[16];
-        s_f1_load_fft_tw_x2<CFG>(ld_first, sm, strip, tid, v);
+        const bool stash_this = kStash && strip < kStashStrips;
+        if (stash_this) {
+          // these strips are not read again: no reason to keep them in L2; columns [64 strip, 64 strip + 64) of this
+          // thread's lane take the 16 quads in the order the combine asks for them: (row J, row J + 8), J = 0..7
+          auto ld_once = [&](size_t off) { return ldg_policy(x4 + off, pol_stream); };
+          const int h1 = tid >> 4, c4 = strip * 16 + (tid & 15);
+          float4 q[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) q[j] = ld_once((size_t)(h1 + CFG::N1h * j) * CFG::M + c4);
+          tmem_st_quads8(tmem_mine + 64u * strip, q[0], q[8], q[1], q[9], q[2], q[10], q[3], q[11]);
+          tmem_st_quads8(tmem_mine + 64u * strip + 32u, q[4], q[12], q[5], q[13], q[6], q[14], q[7], q[15]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = cf2_from(q[j]);
+          tmem_wait_st();
+          s_f1_fft_tw_x2<CFG>(sm, tid, v);
+        } else {
+          s_f1_load_fft_tw_x2<CFG>(ld_first, sm, strip, tid, v);
+        }
         if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -314,7 +416,7 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
       const int next = plane + gridDim.x;
       for (int strip = CFG::nstrips - 1; strip >= 0; --strip) {
         typename CFG::cx_fft8 eva[8], evb[8], oda[8], odb[8];
-        if (strip > 0) prefetch_strip<CFG>(x4, strip - 1, tid, true);
+        if (strip > 0 && !(kStash && strip - 1 < kStashStrips)) prefetch_strip<CFG>(x4, strip - 1, tid, true);
         else if (next < nplanes) prefetch_strip<CFG>(reinterpret_cast<const Quad*>(src + next * plane_px), 0, tid);
         for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 0, u);
         __syncthreads();
@@ -334,11 +436,23 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
           __syncthreads();
           s_inv_fft8<CFG>(sm, tid, 1, oda, odb);
           __syncthreads();
-          s_inv_combine_store<CFG>(ld_again, st, epp, strip, tid, eva, evb, oda, odb);
+          if (kStash && strip < kStashStrips) {
+            const unsigned taddr = tmem_mine + 64u * strip;
+            float4 x0, x1;
+            tmem_ld_quads2(taddr, x0, x1);
+            CombineT<CFG, 0>::run(taddr, st, epp, (size_t)(tid >> 4) * CFG::M + strip * 16 + (tid & 15), x0, x1, eva, evb, oda, odb);
+          } else {
+            s_inv_combine_store<CFG>(ld_again, st, epp, strip, tid, eva, evb, oda, odb);
+          }
         }
       }
     }
     // next plane: its first E write happens after its loads and Z is only rewritten two barriers later
+  }
+  if (kStash) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem_base, kTmemCols);
   }
   // Programmatic dependent launch: this grid may have started before the previous kernel in the stream finished.
   // Do not let it COMPLETE before that kernel has (completion and memory flush), so that whatever the stream runs
@@ -492,6 +606,9 @@ int launch_static_one(const FusedPlan& p, const StaticArgs& a, const EPI& epi, c
     RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::smemBytes));
     RD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::nthreads, CFG::smemBytes));
     if (per_sm < 1) per_sm = 1;
+    // The occupancy API answers 1 for any kernel that contains tcgen05.alloc (cubin attribute TCGEN05_1CTA_USED); two
+    // CTAs that allocate 256 of the 512 columns each do co-reside, and registers and shared memory admit exactly two.
+    if (StashX<CFG, BANK, TIn>::value) per_sm = 2;
   }
   int grid = p.sm_count * per_sm;
   if (grid > a.nplanes) grid = a.nplanes;
