@@ -216,7 +216,11 @@ struct StashX {
 #ifdef RD_NO_TMEM_STASH
   static constexpr bool value = false;
 #else
+#ifdef RD_NO_TMEM_STASH_1CTA
   static constexpr bool value = CFG::kTwoCtas && !BANK && std::is_same<TIn, float>::value;
+#else
+  static constexpr bool value = !BANK && std::is_same<TIn, float>::value;
+#endif
 #endif
 };
 
@@ -277,7 +281,7 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
   // x stash in tensor memory: two-CTAs-per-SM mix kernels with float32 sources (see tmem_* above)
   constexpr bool kStash = StashX<CFG, BANK, TIn>::value;
   constexpr int kStashStrips = 2;                            // strips 0 and 1: read first, re-read last
-  constexpr unsigned kTmemCols = 256;                        // half of the SM's tensor memory per CTA
+  constexpr unsigned kTmemCols = CFG::kTwoCtas ? 256 : 512;   // per CTA: half of the SM's tensor memory, or all of it
   if (kStash && tid < 32) tmem_alloc(smem_u32(sm + CFG::offBar + 16), kTmemCols);
   if (kStash) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -315,22 +319,32 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
       // one CTA per SM (384^2): registers are not capped at 128, so rows j = 0..7 of the next strip are requested
       // one stage early (32 registers in flight across the last exchange stage): the 64 KB load burst of a strip
       // is split in two (+1 % measured).  At two CTAs per SM the same trick spills and loses 4 %.
+      // strips whose x goes to the tensor-memory stash are not read again: no reason to keep them in L2
+      auto ld_strip = [&](int strip) {
+        const unsigned long long pol = (kStash && strip < kStashStrips) ? pol_stream : pol_keep;
+        return [=](size_t off) { return BANK ? ldg_plain(x4 + off) : ldg_policy(x4 + off, pol); };
+      };
       float4 lo[8];
-      s_f1_load_rows<CFG, 0>(ld_first, 0, tid, lo);
+      s_f1_load_rows<CFG, 0>(ld_strip(0), 0, tid, lo);
       for (int strip = 0; strip < CFG::nstrips; ++strip) {
         cf2 v[16];
         {
           float4 hi[8];
-          s_f1_load_rows<CFG, 8>(ld_first, strip, tid, hi);
+          s_f1_load_rows<CFG, 8>(ld_strip(strip), strip, tid, hi);
           if (strip + 1 < CFG::nstrips) prefetch_strip<CFG>(x4, strip + 1, tid);
+          if (kStash && strip < kStashStrips) {     // quads in the order the combine asks for them: (row J, row J + 8)
+            tmem_st_quads8(tmem_mine + 64u * strip, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], lo[3], hi[3]);
+            tmem_st_quads8(tmem_mine + 64u * strip + 32u, lo[4], hi[4], lo[5], hi[5], lo[6], hi[6], lo[7], hi[7]);
+          }
           s_f1_fft_tw_raw_x2<CFG>(sm, tid, lo, hi, v);
+          if (kStash && strip < kStashStrips) tmem_wait_st();
         }
         s_f1_store_half_x2<CFG>(sm, tid, 0, v);
         __syncthreads();
         for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, 0, u);
         __syncthreads();
         s_f1_store_half_x2<CFG>(sm, tid, 1, v);
-        if (strip + 1 < CFG::nstrips) s_f1_load_rows<CFG, 0>(ld_first, strip + 1, tid, lo);
+        if (strip + 1 < CFG::nstrips) s_f1_load_rows<CFG, 0>(ld_strip(strip + 1), strip + 1, tid, lo);
         __syncthreads();
         for (int u = tid; u < 256; u += NT) s_f1_pruned<CFG>(sm, strip, 1, u);
         __syncthreads();
@@ -351,8 +365,8 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
           tmem_st_quads8(tmem_mine + 64u * strip + 32u, q[4], q[12], q[5], q[13], q[6], q[14], q[7], q[15]);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = cf2_from(q[j]);
+          s_f1_fft_tw_x2<CFG>(sm, tid, v);       // the stores to tensor memory drain behind the transform
           tmem_wait_st();
-          s_f1_fft_tw_x2<CFG>(sm, tid, v);
         } else {
           s_f1_load_fft_tw_x2<CFG>(ld_first, sm, strip, tid, v);
         }
@@ -423,14 +437,25 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
         s_inv_fft8<CFG>(sm, tid, 0, eva, evb);
         __syncthreads();
         if constexpr (CFG::smemBytes > 113 * 1024) {
-          // one CTA per SM: request half of the strip's x quads before the second-parity stage
-          float4 xpre[8];
-          s_inv_preload_x<CFG>(ld_again, strip, tid, xpre);
-          for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 1, u);
-          __syncthreads();
-          s_inv_fft8<CFG>(sm, tid, 1, oda, odb);
-          __syncthreads();
-          s_inv_combine_store_pre<CFG>(ld_again, st, epp, strip, tid, xpre, eva, evb, oda, odb);
+          if (kStash && strip < kStashStrips) {     // x of this strip waits in tensor memory
+            for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 1, u);
+            __syncthreads();
+            s_inv_fft8<CFG>(sm, tid, 1, oda, odb);
+            __syncthreads();
+            const unsigned taddr = tmem_mine + 64u * strip;
+            float4 x0, x1;
+            tmem_ld_quads2(taddr, x0, x1);
+            CombineT<CFG, 0>::run(taddr, st, epp, (size_t)(tid >> 4) * CFG::M + strip * 16 + (tid & 15), x0, x1, eva, evb, oda, odb);
+          } else {
+            // one CTA per SM: request half of the strip's x quads before the second-parity stage
+            float4 xpre[8];
+            s_inv_preload_x<CFG>(ld_again, strip, tid, xpre);
+            for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 1, u);
+            __syncthreads();
+            s_inv_fft8<CFG>(sm, tid, 1, oda, odb);
+            __syncthreads();
+            s_inv_combine_store_pre<CFG>(ld_again, st, epp, strip, tid, xpre, eva, evb, oda, odb);
+          }
         } else {
           for (int u = tid; u < 256; u += NT) s_inv_pruned<CFG>(sm, strip, 1, u);
           __syncthreads();
@@ -608,7 +633,7 @@ int launch_static_one(const FusedPlan& p, const StaticArgs& a, const EPI& epi, c
     if (per_sm < 1) per_sm = 1;
     // The occupancy API answers 1 for any kernel that contains tcgen05.alloc (cubin attribute TCGEN05_1CTA_USED); two
     // CTAs that allocate 256 of the 512 columns each do co-reside, and registers and shared memory admit exactly two.
-    if (StashX<CFG, BANK, TIn>::value) per_sm = 2;
+    if (StashX<CFG, BANK, TIn>::value && CFG::kTwoCtas) per_sm = 2;
   }
   int grid = p.sm_count * per_sm;
   if (grid > a.nplanes) grid = a.nplanes;
