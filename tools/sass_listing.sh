@@ -15,8 +15,8 @@ echo
 echo "## opcode histogram (static instruction counts)"
 grep -E '^\s+/\*[0-9a-f]{4}\*/' k.sass | awk '{op=$2; if (op ~ /^@/) op=$3; sub(/\..*/, "", op); sub(/;/, "", op); print op}' | sort | uniq -c | sort -rn
 echo
-echo "## bulk-async copy (TMA engine, non-tensor form: cp.async.bulk -> UBLKCP), mbarrier (SYNCS), programmatic dependent launch (PREEXIT = launch_dependents, ACQBULK = griddepcontrol.wait), L2 prefetch (CCTL.E.PF2)"
-grep -E 'UBLKCP|SYNCS|PREEXIT|ACQBULK|FENCE|CCTL' k.sass | sed 's#/\* 0x[0-9a-f]* \*/##'
+echo "## bulk-async copy (TMA engine, non-tensor form: cp.async.bulk -> UBLKCP), mbarrier (SYNCS), programmatic dependent launch (PREEXIT = launch_dependents, ACQBULK = griddepcontrol.wait), L2 prefetch (CCTL.E.PF2), tensor memory (UTCALLOC / STTM / LDTM = tcgen05.alloc / st / ld)"
+grep -E 'UBLKCP|SYNCS|PREEXIT|ACQBULK|FENCE|CCTL|STTM|LDTM|UTC|TCGEN' k.sass | sed 's#/\* 0x[0-9a-f]* \*/##'
 echo
 printf "packed pairs: FADD2 %s  FMUL2 %s  FFMA2 %s   operand modifiers folded by ptxas: swapped halves (.LO_HI) %s, per-half negation (.NP/.PN) %s, scalar broadcast (.F32 source) %s\n" \
   "$(grep -c 'FADD2' k.sass)" "$(grep -c 'FMUL2' k.sass)" "$(grep -c 'FFMA2' k.sass)" "$(grep -c 'LO_HI' k.sass)" "$(grep -cE '\.(NP|PN)' k.sass)" "$(grep -cE 'R[0-9]+(\.reuse)?\.F32[ ,;]' k.sass)"
