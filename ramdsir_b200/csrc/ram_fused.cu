@@ -292,7 +292,10 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
     // this thread's 128 columns: lane quadrant = warp % 4 (address bits 31:16 = lane), column half = warp / 4
     tmem_mine = tmem_base + ((unsigned)((tid >> 5) & 3) << 21) + (unsigned)(tid >> 7) * 128u;
   }
-  mbar_wait(bar_tab, 0);
+  // The tables are first needed by the twiddles of the first strip: the kernels that stash x issue that strip's loads
+  // before waiting for them (a CTA lives for 2-3 planes, so its prologue is worth hiding).
+  bool tables_pending = kStash;
+  if (!tables_pending) mbar_wait(bar_tab, 0);
   unsigned patch_parity = 0;
   constexpr size_t plane_px = (size_t)CFG::H * CFG::W;
   constexpr int patch_px = CFG::nb * CFG::nb;
@@ -326,6 +329,10 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
       };
       float4 lo[8];
       s_f1_load_rows<CFG, 0>(ld_strip(0), 0, tid, lo);
+      if (tables_pending) {
+        mbar_wait(bar_tab, 0);
+        tables_pending = false;
+      }
       for (int strip = 0; strip < CFG::nstrips; ++strip) {
         cf2 v[16];
         {
@@ -361,6 +368,10 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
           float4 q[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) q[j] = ld_once((size_t)(h1 + CFG::N1h * j) * CFG::M + c4);
+          if (tables_pending) {
+            mbar_wait(bar_tab, 0);
+            tables_pending = false;
+          }
           tmem_st_quads8(tmem_mine + 64u * strip, q[0], q[8], q[1], q[9], q[2], q[10], q[3], q[11]);
           tmem_st_quads8(tmem_mine + 64u * strip + 32u, q[4], q[12], q[5], q[13], q[6], q[14], q[7], q[15]);
 #pragma unroll
