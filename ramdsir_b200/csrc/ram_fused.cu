@@ -208,6 +208,13 @@ struct MixScalars {
   float dscale;    // EpiSat: 1 / (hi - lo), folded into dF;  EpiClamp: 1
   float dc_add;    // EpiSat: -lo / (hi - lo), added to the DC bin of dF / (H W);  EpiClamp: 0
   float cscale, cshift;   // fused dual output: clean = x * cscale + cshift
+  // Completion watermark (see "automatic overlap" below).  A CTA of launch number `seq` that has passed the
+  // griddepcontrol.wait at its end knows that launch seq - 1 is complete and flushed, and raises *complete_upto to seq
+  // ("every launch before seq is complete").  A launch that may overlap its predecessors first waits until the
+  // watermark has reached wait_upto = seq - 2, i.e. until the launch three back is complete: at most the launches one
+  // and two back can be alive beside it.
+  unsigned long long* complete_upto;
+  unsigned long long seq, wait_upto;     // wait_upto == 0: nothing to wait for
 };
 
 // which static kernels stash x in tensor memory (-DRD_NO_TMEM_STASH: none, for A/B runs)
@@ -282,6 +289,12 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
     mbar_init_fence();
     mbar_expect_tx(bar_tab, CFG::tabBytes);
     bulk_g2s(smem_u32(sm + CFG::offTab), tables, CFG::tabBytes, bar_tab);
+    if (ms.wait_upto) {            // the launch three back must be complete (it is, unless a CTA of it straggles)
+      unsigned long long seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(ms.complete_upto) : "memory");
+      } while (seen < ms.wait_upto);
+    }
   }
   // x stash in tensor memory: two-CTAs-per-SM mix kernels with float32 sources (see tmem_* above)
   constexpr bool kStash = StashX<CFG, BANK, TIn>::value;
@@ -501,6 +514,8 @@ ram_fused_static_kernel(const TIn* __restrict__ src, const float* __restrict__ b
   // Do not let it COMPLETE before that kernel has (completion and memory flush), so that whatever the stream runs
   // next (a copy of the previous batch, a consumer kernel) is ordered after both.  No-op for a plain launch.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // the previous launch in the stream (number seq - 1) is now complete and flushed: raise the watermark
+  if (tid == 0) asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" :: "l"(ms.complete_upto), "l"(ms.seq) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -556,17 +571,31 @@ int get_plan(int H, int W, int b, bool runtime_shape, FusedPlan** out) {
 }
 
 // ---- automatic overlap of consecutive launches -------------------------------------------------------------
-// A static fused launch may start while the previous fused launch in the same stream drains its last wave
-// (programmatic dependent launch) when the two touch disjoint memory: nothing this launch reads or writes was written
-// by that launch, and nothing it writes was read by it.  The library knows every buffer of both launches, so it
-// decides this itself; the caller's RAMDSIR_FLAG_INDEPENDENT only skips the check.  The last TWO launches are
-// compared because launch N+2 can start as soon as N+1 has started all its CTAs, i.e. when N's CTAs have exited but
-// before N is formally complete.  Anything else the library enqueues on the stream clears the trail.
+// A static fused launch may start while the previous fused launches in the same stream drain their last CTAs
+// (programmatic dependent launch) when they touch disjoint memory: nothing this launch reads or writes was written by
+// them, and nothing it writes was read by them.  The library knows every buffer of every launch, so it decides this
+// itself; the caller's RAMDSIR_FLAG_INDEPENDENT only skips the check.  A dependent launch is dispatched once its
+// predecessor has dispatched all its CTAs, not once older launches have retired theirs, so CTAs of the launches one
+// AND two back can still be running: the last kTrailDepth = 2 launches are compared, and the completion watermark
+// (Tickets, below) makes every launch wait until the launch three back is complete, so that nothing older can be
+// alive.  Anything else the library enqueues on the stream clears the trail (the next launch is then a plain,
+// fully ordered one).
 struct Range { uintptr_t lo, hi; };
 struct LaunchFootprint { Range rd[4]; int nrd = 0; Range wr[2]; int nwr = 0; };
-struct Trail { LaunchFootprint last[2]; int n = 0; };
+constexpr int kTrailDepth = 2;
+struct Trail { LaunchFootprint last[kTrailDepth]; int n = 0; };
 std::mutex g_trail_mu;
 std::map<std::pair<int, cudaStream_t>, Trail> g_trails;
+
+// Completion watermark: one monotonic device word per (device, stream), "every launch numbered below this is complete"
+// (numbers start at 1).  Never freed or reset (8 bytes per stream).
+struct Tickets {
+  unsigned long long* complete_upto = nullptr;   // device
+  unsigned long long seq = 1;                     // number of the next launch
+  unsigned long long plain_seq = 1;               // number of the most recent launch WITHOUT overlap permission (it
+                                                  // starts after everything before it has completed)
+};
+std::map<std::pair<int, cudaStream_t>, Tickets> g_tickets;   // guarded by g_trail_mu
 
 bool overlaps(const Range& a, const Range& b) { return a.lo < b.hi && b.lo < a.hi; }
 bool conflicts(const LaunchFootprint& cur, const LaunchFootprint& prev) {
@@ -589,10 +618,35 @@ bool trail_push(int dev, cudaStream_t st, const LaunchFootprint& cur, bool assum
     ok = g_auto_overlap;
     for (int i = 0; ok && i < t.n; ++i) ok = !conflicts(cur, t.last[i]);
   }
-  t.last[1] = t.last[0];
+  for (int i = kTrailDepth - 1; i > 0; --i) t.last[i] = t.last[i - 1];
   t.last[0] = cur;
-  if (t.n < 2) ++t.n;
+  if (t.n < kTrailDepth) ++t.n;
   return ok;
+}
+// Numbers the launch and, when it may overlap its predecessors (pdl), tells it which watermark to wait for.
+int ticket_take(int dev, cudaStream_t st, bool pdl, MixScalars& ms) {
+  std::lock_guard<std::mutex> lk(g_trail_mu);
+  Tickets& t = g_tickets[{dev, st}];
+  if (!t.complete_upto) {   // once per (device, stream): zeroed on the private upload stream, which alone is synchronised
+    cudaStream_t up = nullptr;
+    {
+      std::lock_guard<std::mutex> lk2(g_mu);
+      cudaStream_t& u = g_upload_stream[dev];
+      if (!u) RD_CUDA(cudaStreamCreateWithFlags(&u, cudaStreamNonBlocking));
+      up = u;
+    }
+    RD_CUDA(cudaMalloc(&t.complete_upto, sizeof(unsigned long long)));
+    RD_CUDA(cudaMemsetAsync(t.complete_upto, 0, sizeof(unsigned long long), up));
+    RD_CUDA(cudaStreamSynchronize(up));
+  }
+  const unsigned long long q = t.seq++;
+  if (!pdl) t.plain_seq = q;
+  ms.complete_upto = t.complete_upto;
+  ms.seq = q;
+  // launches q - 2, q - 1 and q all overlap their predecessors: q - 3 (and everything older) must be complete, which a
+  // CTA of launch q - 2 announces (watermark >= q - 2) when it has passed its final griddepcontrol.wait
+  ms.wait_upto = (pdl && t.plain_seq + 3 <= q) ? q - 2 : 0;
+  return RAMDSIR_OK;
 }
 }  // namespace
 
@@ -655,6 +709,20 @@ int launch_static_one(const FusedPlan& p, const StaticArgs& a, const EPI& epi, c
   }
   int grid = p.sm_count * per_sm;
   if (grid > a.nplanes) grid = a.nplanes;
+  // A launch that may overlap its predecessor does not need to fill every CTA slot itself: the neighbouring launches
+  // take the rest.  Give every CTA the same number of planes instead (768 planes: 256 CTAs x 3 rather than 176 x 3 +
+  // 120 x 2) -- fewer CTA prologues and no short CTAs; +1.0 % on the two-CTAs-per-SM kernels (measured: -0.75 % on the
+  // 384^2 kernel and worse for grids far below the slot count, hence the conditions).
+  if (pdl && CFG::kTwoCtas) {
+    const int rounds = (a.nplanes + grid - 1) / grid;
+    const int balanced = (a.nplanes + rounds - 1) / rounds;
+    if (balanced * 5 >= grid * 4) grid = balanced;
+  }
+  MixScalars msl = ms;
+  {
+    const int rc = ticket_take(dev, st, pdl, msl);
+    if (rc) return rc;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(CFG::nthreads);
@@ -665,7 +733,7 @@ int launch_static_one(const FusedPlan& p, const StaticArgs& a, const EPI& epi, c
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  RD_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<const TIn*>(a.src), a.bank, a.pidx, a.rk, a.out, epi, ms,
+  RD_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<const TIn*>(a.src), a.bank, a.pidx, a.rk, a.out, epi, msl,
                              (const float*)p.tables, a.clean));
   count_launch();
   RD_CUDA(cudaGetLastError());
@@ -680,7 +748,7 @@ int launch_static(const FusedPlan& p, const StaticArgs& a, cudaStream_t st) {
   auto rng = [](const void* q, size_t n) { return Range{reinterpret_cast<uintptr_t>(q), reinterpret_cast<uintptr_t>(q) + n}; };
   LaunchFootprint fp;
   fp.rd[fp.nrd++] = rng(a.src, a.src_bytes);
-  MixScalars ms{a.ratio_den, a.n_bank, a.C, a.nplanes, 1.f, 0.f, a.ep.scale, a.ep.shift};
+  MixScalars ms{a.ratio_den, a.n_bank, a.C, a.nplanes, 1.f, 0.f, a.ep.scale, a.ep.shift, nullptr, 0ull, 0ull};
   if (BANK) {
     fp.wr[fp.nwr++] = rng(a.out, (size_t)a.nplanes * patch_bytes);
     trail_push(dev, st, fp, false);       // recorded (a following mix reads this bank); itself a plain launch
