@@ -578,6 +578,38 @@ def test_auto_overlap_keeps_stream_order_between_dependent_launches(R):
         assert torch.equal(o, ref) and s_.item() == ref.double().sum().item()
 
 
+def test_overlapped_launches_three_back_share_buffers(R):
+    """A long run of overlapping launches that rotate over three output buffers and feed results back in: launch i
+    writes the buffer launch i - 3 wrote, and every fourth launch reads what was produced three launches earlier -- beyond
+    the two launches the library compares; the completion watermark orders those.  Every buffer must end up exactly as in the
+    strictly serial run."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B, C, H, W = 256, 3, 256, 256
+    srcs = [torch.rand(B, C, H, W, device="cuda", generator=g) * 255 for _ in range(2)]
+    bank = R.build_amp_bank(torch.rand(8, C, H, W, device="cuda", generator=g) * 255)
+    rs = np.random.RandomState(5)
+    pidx = torch.from_numpy(rs.randint(0, 8, B)).cuda()
+    rks = [torch.from_numpy(rs.randint(1, 10, B).astype(np.int32)).cuda() for _ in range(5)]
+
+    def run(**kw):
+        outs = [torch.zeros(B, C, H, W, device="cuda") for _ in range(3)]
+        for i in range(24):
+            # every fourth launch reads the buffer written three launches earlier (and two launches back its writer
+            # is no longer in the compared window)
+            src = outs[(i - 3) % 3] if (i >= 3 and i % 4 == 3) else srcs[i % 2]
+            if src is outs[i % 3]:
+                src = srcs[i % 2]
+            R.ram_mix_batch(src, bank, pidx, rks[i % 5], out=outs[i % 3], **kw)
+        torch.cuda.synchronize()
+        return outs
+
+    want = run(serial=True)
+    for _ in range(3):
+        got = run()
+        for a, b2 in zip(got, want):
+            assert torch.equal(a, b2)
+
+
 def test_patch_staging_handles_unaligned_bank_rows(R):
     """The partner's patch reaches shared memory through a 16-byte-granular bulk copy; bank rows start on arbitrary
     4-byte boundaries (10 404 B per fundus patch) and the bank itself may be an odd slice of a gather buffer."""
