@@ -316,8 +316,8 @@ RD_HD void m_band(const float4* R, float2* D, const float* tab, const float* pat
   // `patch` points at the two staged rows of this kh pair: [0] = row b + kh, [1] = row b - kh (shared memory)
   const float at = 0.5f * (patch[srow * CFG::nb + (kw + CFG::b)] + patch[(kh == 0 ? 0 : 1 - srow) * CFG::nb + (CFG::b - kw)]);
   cf d;
-  if (a2 > 0.f) {
-    const float s = one_minus_ratio * (at / sqrtf(a2) - 1.0f) * CFG::invHW;
+  if (a2 >= 1.17549435e-38f) {       // a normal float (see s_band_mix)
+    const float s = one_minus_ratio * (at * rd_rsqrt(a2) - 1.0f) * CFG::invHW;
     d = cf{f.re * s, f.im * s};
   } else {
     d = cf{one_minus_ratio * at * CFG::invHW, 0.f};
