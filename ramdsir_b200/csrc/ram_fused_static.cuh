@@ -59,8 +59,8 @@ struct SCfg {
   static constexpr int prawBytes = s_al16(pBytes + 16);
   static constexpr int offPraw = offD + s_al16(dBytes);
   static_assert(s_al16(dBytes) + prawBytes <= eBytes, "D and the patch landing zone must fit inside E");
-  static constexpr int offBar = offTab + tabBytes;      // two mbarriers (tables, patch)
-  static constexpr int smemBytes = offBar + 16;
+  static constexpr int offBar = offTab + tabBytes;      // two mbarriers (tables, patch) + the TMEM base address slot
+  static constexpr int smemBytes = offBar + 32;
   static constexpr float invHW = (float)(1.0 / ((double)H_ * (double)W_));
   // Complex arithmetic of each phase: cf = scalar FADD / FMUL / FFMA, cp = (re, im) register pairs on FADD2 / FMUL2 /
   // FFMA2 (ram_math_x2.cuh): half the issue slots for the same FP-pipe time -- and scalar butterflies can use both FP
