@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(CFG::bThreads) ram_mp_pass_b(float4* __restric
     const int64_t* __restrict__ pidx, const int32_t* __restrict__ rk, int ratio_den, int n_bank, int C, float* __restrict__ bank_out,
     const float* __restrict__ tab_b, int plane0, float dscale, float dc_add) {
   extern __shared__ __align__(16) unsigned char sm[];
-  const int tid = threadIdx.x, kg = blockIdx.x % CFG::nkg, plane = blockIdx.x / CFG::nkg;
+  // Planes in REVERSE launch order: pass A wrote the band rows of the last planes most recently, so pass B starts where
+  // they are still in L2 -- and finishes with the first planes, which is where pass C (forward order) starts reading.
+  const int tid = threadIdx.x, kg = blockIdx.x % CFG::nkg, plane = (int)(gridDim.x / CFG::nkg) - 1 - (int)(blockIdx.x / CFG::nkg);
   float4* t = reinterpret_cast<float4*>(sm + CFG::bOffTab);
   for (int i = tid; i < CFG::bTabBytes / 16; i += CFG::bThreads) t[i] = reinterpret_cast<const float4*>(tab_b)[i];
   __syncthreads();
