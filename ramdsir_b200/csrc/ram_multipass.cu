@@ -179,10 +179,12 @@ __global__ void __launch_bounds__(256, 2) ram_mp_pass_a(const float* __restrict_
   const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, plane = blockIdx.x / CFG::nstrips;
   float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
   for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
-  unsigned long long pol_keep;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  // x of a whole-batch pass is far larger than L2 and is not met again before it has been evicted: stream it, and leave
+  // L2 to the band rows that pass B is about to read
+  unsigned long long pol_x;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_x));
   __syncthreads();
-  mp_task_a<CFG>(sm, src, Zg + (size_t)plane * CFG::nb * CFG::M, plane, strip, pol_keep);
+  mp_task_a<CFG>(sm, src, Zg + (size_t)plane * CFG::nb * CFG::M, plane, strip, pol_x);
 }
 template <class CFG, bool BANK>
 __global__ void __launch_bounds__(CFG::bThreads) ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank,
