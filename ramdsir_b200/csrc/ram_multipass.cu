@@ -21,6 +21,43 @@ __device__ __forceinline__ void mp_stg_policy(float4* p, float4 v, unsigned long
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
 }
 
+// ---- latency hiding, tuned per shape on the device (same-box A/B, tools/kbench.py) --------------
+//  pf_c       pass C pulls polyphase sub-column p + 1 of x into L2 while it transforms sub-column p (and sub-column 0
+//             while it loads its band rows): 1024^2 -4.1 %
+//  pf_a       the same in pass A, issued behind the loads of sub-column p: 1024^2 -1.5 %, 512^2 +0.3 %
+//  pf_a_next  pass A, in its last sub-column, pulls sub-column 0 of the block that will follow it on its slot
+//             (blocks are dealt in index order, kMpSlots are resident): 1024^2 -1.2 %, 512^2 +-0
+//  pdl        passes B and C are launched as programmatic dependents of the pass before them: their CTAs take the slots
+//             its last wave vacates, load their tables (pass C: start on x) and only then wait for its results.
+//             512^2 -2.2 %, 1024^2 +3.7 % (slower)
+// Deeper prefetch (two sub-columns ahead +4 %, the whole strip at entry +11 %) and the next-block prefetch in pass C
+// (+2 %) were slower; the next block's band rows in pass B gave -0.3 % and were not kept.
+template <class CFG>
+struct MpTune {
+  static constexpr bool pf_c = true;
+  static constexpr bool pf_a = CFG::H > 512;
+  static constexpr bool pf_a_next = CFG::H > 512;
+  static constexpr bool pdl = CFG::H <= 512;
+};
+constexpr int kMpSlots = 296;   // CTAs of pass A resident at once (2 per SM)
+template <class CFG> __device__ __forceinline__ void mp_release_dependents() { if (MpTune<CFG>::pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class CFG> __device__ __forceinline__ void mp_wait_predecessor() { if (MpTune<CFG>::pdl) asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// One polyphase sub-column (256 rows x 256 B of this strip) into L2: two 128-byte lines a thread.
+template <class CFG>
+__device__ __forceinline__ void mp_prefetch_phase(const float4* x4, int strip, int p, int tid) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int line = tid + 256 * k, r = line >> 1;
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(x4 + (size_t)(r * CFG::HP + p) * CFG::M + strip * 16 + (line & 1) * 8));
+  }
+}
+template <class CFG>
+__device__ __forceinline__ void mp_prefetch_next_block(const float* src_chunk, int tid) {
+  const unsigned nb = blockIdx.x + kMpSlots;
+  if (nb < gridDim.x)
+    mp_prefetch_phase<CFG>(reinterpret_cast<const float4*>(src_chunk + (size_t)(nb / CFG::nstrips) * CFG::H * CFG::W), nb % CFG::nstrips, 0, tid);
+}
+
 // ===== task bodies (one CTA each).  `zg` is the plane's band rows in the workspace: [nb][M] float4, read with
 // ld.global.cg (they are produced by other CTAs and have no reuse in L1). ============================================
 
@@ -33,7 +70,9 @@ __device__ __forceinline__ void mp_task_a(unsigned char* sm, const float* __rest
   auto ld = [&](size_t off) { return mp_ldg_policy(x4 + off, pol_keep); };
   for (int p = 0; p < CFG::HP; ++p) {
     cf2 v[16];
+    if (MpTune<CFG>::pf_a_next && p + 1 == CFG::HP) mp_prefetch_next_block<CFG>(src, tid);
     m_f1_load_fft_tw_x2<CFG>(ld, sm, strip, p, tid, v);
+    if (MpTune<CFG>::pf_a && p + 1 < CFG::HP) mp_prefetch_phase<CFG>(x4, strip, p + 1, tid);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       s_f1_store_half_x2<CFG>(sm, tid, half, v);
@@ -142,6 +181,10 @@ __device__ __forceinline__ void mp_task_c(unsigned char* sm, const float* __rest
                                           const int64_t* __restrict__ pidx, int n_bank, int C, float* __restrict__ out,
                                           EPI ep, int plane, int gplane, int strip, unsigned long long pol_stream) {
   const int tid = threadIdx.x;
+  const size_t plane_px = (size_t)CFG::H * CFG::W;
+  const float4* x4 = reinterpret_cast<const float4*>(src + plane * plane_px);
+  if (MpTune<CFG>::pf_c) mp_prefetch_phase<CFG>(x4, strip, 0, tid);
+  mp_wait_predecessor<CFG>();
   {
     float4* Zs = reinterpret_cast<float4*>(sm + CFG::offZ);
     const float4* zg = zgp + strip * 16;
@@ -152,14 +195,13 @@ __device__ __forceinline__ void mp_task_c(unsigned char* sm, const float* __rest
     if (p < 0 || p >= (long long)n_bank) ep = mp_poisoned(ep);
   }
   __syncthreads();
-  const size_t plane_px = (size_t)CFG::H * CFG::W;
-  const float4* x4 = reinterpret_cast<const float4*>(src + plane * plane_px);
   float4* y4 = reinterpret_cast<float4*>(out + plane * plane_px);
   auto ld = [&](size_t off) { return mp_ldg_policy(x4 + off, pol_stream); };
   auto st = [&](size_t off, float4 v) { mp_stg_policy(y4 + off, v, pol_stream); };
   const int h1 = tid >> 4, c4 = strip * 16 + (tid & 15);
   for (int p = 0; p < CFG::HP; ++p) {
     cp eva[8], evb[8], oda[8], odb[8];
+    if (MpTune<CFG>::pf_c && p + 1 < CFG::HP) mp_prefetch_phase<CFG>(x4, strip, p + 1, tid);
     m_inv_pruned<CFG>(sm, p, 0, tid);
     __syncthreads();
     s_inv_fft8<CFG>(sm, tid, 0, eva, evb);
@@ -177,6 +219,7 @@ template <class CFG>
 __global__ void __launch_bounds__(256, 2) ram_mp_pass_a(const float* __restrict__ src, float4* __restrict__ Zg, const float* __restrict__ tab_ac) {
   extern __shared__ __align__(16) unsigned char sm[];
   const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, plane = blockIdx.x / CFG::nstrips;
+  mp_release_dependents<CFG>();
   float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
   for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
   // x of a whole-batch pass is far larger than L2 and is not met again before it has been evicted: stream it, and leave
@@ -194,8 +237,10 @@ __global__ void __launch_bounds__(CFG::bThreads) ram_mp_pass_b(float4* __restric
   // Planes in REVERSE launch order: pass A wrote the band rows of the last planes most recently, so pass B starts where
   // they are still in L2 -- and finishes with the first planes, which is where pass C (forward order) starts reading.
   const int tid = threadIdx.x, kg = blockIdx.x % CFG::nkg, plane = (int)(gridDim.x / CFG::nkg) - 1 - (int)(blockIdx.x / CFG::nkg);
+  mp_release_dependents<CFG>();
   float4* t = reinterpret_cast<float4*>(sm + CFG::bOffTab);
   for (int i = tid; i < CFG::bTabBytes / 16; i += CFG::bThreads) t[i] = reinterpret_cast<const float4*>(tab_b)[i];
+  mp_wait_predecessor<CFG>();
   __syncthreads();
   // `plane` indexes this chunk's workspace and (bank mode) output; plane0 + plane is the batch-global plane whose
   // image selects the partner and the ratio
@@ -293,17 +338,32 @@ int run(bool bank_mode, const MixArgs& a, float* bank_out, int nimg, void* ws, s
     const int n = (planes - p0 < chunk_planes<CFG>()) ? planes - p0 : chunk_planes<CFG>();
     // chunks start on image boundaries only if chunk_planes is a multiple of C; pass plane offsets through pointers
     const float* src = a.src + (size_t)p0 * plane_px;
+    // pass A is an ordinary launch (ordered after whatever precedes it in the stream); B and C may chain on it (MpTune::pdl)
+    cudaLaunchAttribute chain[1];
+    chain[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    chain[0].val.programmaticStreamSerializationAllowed = 1;
+    auto cfg_of = [&](int grid, int threads, size_t smem) {
+      cudaLaunchConfig_t c{};
+      c.gridDim = dim3(grid); c.blockDim = dim3(threads); c.dynamicSmemBytes = smem; c.stream = st;
+      c.attrs = chain; c.numAttrs = MpTune<CFG>::pdl ? 1 : 0;
+      return c;
+    };
     ram_mp_pass_a<CFG><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(src, Zg, pl->tab_ac);
     if (bank_mode) {
-      ram_mp_pass_b<CFG, true><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, nullptr, nullptr, nullptr, 10, 0, a.C, bank_out + (size_t)p0 * patch_px, pl->tab_b, 0, 1.f, 0.f);
+      const cudaLaunchConfig_t cb = cfg_of(n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes);
+      RD_CUDA(cudaLaunchKernelEx(&cb, ram_mp_pass_b<CFG, true>, Zg, (const float*)nullptr, (const int64_t*)nullptr, (const int32_t*)nullptr, 10, 0, a.C,
+                                 bank_out + (size_t)p0 * patch_px, (const float*)pl->tab_b, 0, 1.f, 0.f));
       count_launch(2);
     } else {
-      ram_mp_pass_b<CFG, false><<<n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes, st>>>(Zg, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, nullptr, pl->tab_b, p0, dscale, dc_add);
+      const cudaLaunchConfig_t cb = cfg_of(n * CFG::nkg, CFG::bThreads, CFG::bSmemBytes), cc = cfg_of(n * CFG::nstrips, 256, CFG::smemBytes);
+      RD_CUDA(cudaLaunchKernelEx(&cb, ram_mp_pass_b<CFG, false>, Zg, a.bank, a.pidx, a.rk, a.ratio_den, a.n_bank, a.C, (float*)nullptr,
+                                 (const float*)pl->tab_b, p0, dscale, dc_add));
+      float* outp = a.out + (size_t)p0 * plane_px;
       if (sat)
-        ram_mp_pass_c<CFG, EpiSat><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(src, Zg, a.pidx, a.n_bank, a.C, a.out + (size_t)p0 * plane_px, es, pl->tab_ac, p0);
+        RD_CUDA(cudaLaunchKernelEx(&cc, ram_mp_pass_c<CFG, EpiSat>, src, (const float4*)Zg, a.pidx, a.n_bank, a.C, outp, es, (const float*)pl->tab_ac, p0));
       else
-        ram_mp_pass_c<CFG, EpiClamp><<<n * CFG::nstrips, 256, CFG::smemBytes, st>>>(src, Zg, a.pidx, a.n_bank, a.C, a.out + (size_t)p0 * plane_px,
-                                                                                     EpiClamp{a.ep.lo, a.ep.hi, a.ep.scale, a.ep.shift}, pl->tab_ac, p0);
+        RD_CUDA(cudaLaunchKernelEx(&cc, ram_mp_pass_c<CFG, EpiClamp>, src, (const float4*)Zg, a.pidx, a.n_bank, a.C, outp,
+                                   EpiClamp{a.ep.lo, a.ep.hi, a.ep.scale, a.ep.shift}, (const float*)pl->tab_ac, p0));
       count_launch(3);
     }
   }
