@@ -102,9 +102,27 @@ __device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, f
   // row slot r = 2 g + s  <->  band row  b + kh (s = 0)  /  b - kh (s = 1),  kh = kh0 + g  (kh = 0 uses s = 0 only)
   auto zrow = [&](int r) { const int kh = kh0 + (r >> 1); return zplane + (size_t)(CFG::b + ((r & 1) ? -kh : kh)) * M; };
   auto live = [&](int r) { return !((r & 1) && kh0 + (r >> 1) == 0); };
-  for (int i = tid; i < ng * 2 * M; i += NT) {
-    const int r = i / M, m = i % M;
-    if (live(r)) R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)] = __ldcg(zrow(r) + m);
+  // column m = tid + NT k of a row lives at slot (m % N1w) + SP (m / N1w): a per-thread base plus a constant step.
+  // All loads of the task are issued before the first of them is stored (16 float4 in flight per thread at 1024^2).
+  static_assert(M % NT == 0 && NT % CFG::N1w == 0, "row <-> thread mapping");
+  constexpr int CPT = M / NT, slotK = CFG::SP * (NT / CFG::N1w);
+  const int slot0 = (tid % CFG::N1w) + CFG::SP * (tid / CFG::N1w);
+  {
+    float4 q[2 * KG][CPT];
+#pragma unroll
+    for (int r = 0; r < 2 * KG; ++r)
+      if (r < 2 * ng && live(r)) {
+        const float4* z = zrow(r) + tid;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) q[r][k] = __ldcg(z + NT * k);
+      }
+#pragma unroll
+    for (int r = 0; r < 2 * KG; ++r)
+      if (r < 2 * ng && live(r)) {
+        float4* Rr = R + (size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + slot0;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) Rr[slotK * k] = q[r][k];
+      }
   }
   // stage the partner-patch rows b + kh and b - kh of every kh handled here (coalesced; consumed by the band tasks)
   float omr = 0.f;
@@ -115,10 +133,15 @@ __device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, f
     omr = ok ? (float)(ratio_den - rk[img]) / (float)ratio_den * dscale : __int_as_float(0x7fc00000);
     const float* patch = bank + ((size_t)(ok ? p : 0) * C + ch) * ((size_t)CFG::nb * CFG::nb);
     float* P = reinterpret_cast<float*>(sm + CFG::bOffP);
-    for (int i = tid; i < ng * 2 * CFG::nb; i += NT) {
-      const int r = i / CFG::nb, j = i % CFG::nb, kh = kh0 + (r >> 1);
-      P[i] = patch[(size_t)(CFG::b + ((r & 1) ? -kh : kh)) * CFG::nb + j];
-    }
+#pragma unroll
+    for (int r = 0; r < 2 * KG; ++r)
+      if (r < 2 * ng) {
+        const int kh = kh0 + (r >> 1);
+        const float* prow = patch + (size_t)(CFG::b + ((r & 1) ? -kh : kh)) * CFG::nb;
+#pragma unroll
+        for (int k = 0; k < (CFG::nb + NT - 1) / NT; ++k)
+          if (tid + NT * k < CFG::nb) P[r * CFG::nb + tid + NT * k] = prow[tid + NT * k];
+      }
   }
   __syncthreads();
   for (int t = tid; t < ng * 2 * CFG::N1w; t += NT) {
@@ -165,10 +188,14 @@ __device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, f
       if (live(2 * g + tt / CFG::N1w)) m_row_stage1<CFG, 1>(R + (size_t)g * RP, tab, tt);
     }
     __syncthreads();
-    for (int i = tid; i < ng * 2 * M; i += NT) {
-      const int r = i / M, m = i % M;
-      if (live(r)) zrow(r)[m] = R[(size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + (m % CFG::N1w) + CFG::SP * (m / CFG::N1w)];
-    }
+#pragma unroll
+    for (int r = 0; r < 2 * KG; ++r)
+      if (r < 2 * ng && live(r)) {
+        const float4* Rr = R + (size_t)(r >> 1) * RP + (r & 1) * CFG::rowPitch + slot0;
+        float4* z = zrow(r) + tid;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) z[NT * k] = Rr[slotK * k];
+      }
   }
 }
 
@@ -241,7 +268,7 @@ __global__ void __launch_bounds__(CFG::bThreads) ram_mp_pass_b(float4* __restric
   float4* t = reinterpret_cast<float4*>(sm + CFG::bOffTab);
   for (int i = tid; i < CFG::bTabBytes / 16; i += CFG::bThreads) t[i] = reinterpret_cast<const float4*>(tab_b)[i];
   mp_wait_predecessor<CFG>();
-  __syncthreads();
+  // no barrier here: the task reads the tables only behind its own first barrier, so their loads overlap its row loads
   // `plane` indexes this chunk's workspace and (bank mode) output; plane0 + plane is the batch-global plane whose
   // image selects the partner and the ratio
   mp_task_b<CFG, BANK, CFG::bThreads>(sm, reinterpret_cast<const float*>(sm + CFG::bOffTab), Zg + (size_t)plane * CFG::nb * CFG::M,

@@ -3,7 +3,7 @@
 
   cuobjdump -xelf all ramdsir_b200/libramdsir.so ; nvdisasm -gi -c ram_fused.sm_100a.cubin > fused_gi.sass
   ncu -i prof.ncu-rep --page source --csv > src.csv
-  python tools/ncu_by_phase.py fused_gi.sass <mangled-kernel-substring> src.csv [top_file.cu]
+  python tools/ncu_by_phase.py fused_gi.sass <mangled-kernel-substring> src.csv [top_file.cu [first-last line]]
 
 Groups executed warp-instructions and stall samples by the OUTERMOST source line (the call site in
 the kernel body), i.e. by phase of the fused pipeline.
@@ -12,6 +12,7 @@ import collections, csv, re, sys
 
 sass_file, kernel_pat, ncu_csv = sys.argv[1:4]
 top_file = sys.argv[4] if len(sys.argv) > 4 else "ram_fused.cu"
+lo_line, hi_line = (int(v) for v in sys.argv[5].split("-")) if len(sys.argv) > 5 else (0, 1 << 30)   # e.g. a task body's lines
 in_k, chain, seq = False, [], []
 for ln in open(sass_file):
     if ".section" in ln and ".text." in ln:
@@ -44,7 +45,7 @@ tot_i = tot_s = 0
 for r, (addr, txt, ch) in zip(data, seq):
     assert int(r[0], 16) - base == addr
     ie, sm = int(r[ix["Instructions Executed"]]), int(r[ix["# Samples"]])
-    outer = [c for c in ch if c[0] == top_file]
+    outer = [c for c in ch if c[0] == top_file and lo_line <= c[1] <= hi_line]
     key = outer[-1][1] if outer else -1
     a = agg[key]
     a[0] += ie
