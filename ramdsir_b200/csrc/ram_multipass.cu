@@ -64,14 +64,20 @@ __device__ __forceinline__ void mp_prefetch_next_block(const float* src_chunk, i
 // ---- A: forward columns of one (plane, strip) -> zg[kh][strip columns] ------------------------------------------
 template <class CFG>
 __device__ __forceinline__ void mp_task_a(unsigned char* sm, const float* __restrict__ src, float4* __restrict__ zgp,
-                                          int plane, int strip, unsigned long long pol_keep) {
+                                          int plane, int strip, unsigned long long pol_keep, const float* __restrict__ tab_ac) {
   const int tid = threadIdx.x;
   const float4* x4 = reinterpret_cast<const float4*>(src + (size_t)plane * CFG::H * CFG::W);
   auto ld = [&](size_t off) { return mp_ldg_policy(x4 + off, pol_keep); };
   for (int p = 0; p < CFG::HP; ++p) {
     cf2 v[16];
     if (MpTune<CFG>::pf_a_next && p + 1 == CFG::HP) mp_prefetch_next_block<CFG>(src, tid);
-    m_f1_load_fft_tw_x2<CFG>(ld, sm, strip, p, tid, v);
+    m_f1_load_rows_x2<CFG>(ld, strip, p, tid, v);
+    if (p == 0) {   // the tables travel behind the first sub-column's loads
+      float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
+      for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
+      __syncthreads();
+    }
+    s_f1_fft_tw_x2<CFG>(sm, tid, v);
     if (MpTune<CFG>::pf_a && p + 1 < CFG::HP) mp_prefetch_phase<CFG>(x4, strip, p + 1, tid);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -81,9 +87,17 @@ __device__ __forceinline__ void mp_task_a(unsigned char* sm, const float* __rest
       __syncthreads();
     }
   }
-  const float4* Zs = reinterpret_cast<const float4*>(sm + CFG::offZ);
-  float4* zg = zgp + strip * 16;
-  for (int i = tid; i < CFG::nb * 16; i += 256) zg[(size_t)(i >> 4) * CFG::M + (i & 15)] = Zs[(i >> 4) * CFG::pitchZ + (i & 15)];
+  // element i = tid + 256 k of the strip's band rows is row (tid >> 4) + 16 k, column tid & 15
+  const float4* Zs = reinterpret_cast<const float4*>(sm + CFG::offZ) + (tid >> 4) * CFG::pitchZ + (tid & 15);
+  float4* zg = zgp + strip * 16 + (size_t)(tid >> 4) * CFG::M + (tid & 15);
+  constexpr int NZ = (CFG::nb + 15) / 16;
+  float4 q[NZ];
+#pragma unroll
+  for (int k = 0; k < NZ; ++k)
+    if ((tid >> 4) + 16 * k < CFG::nb) q[k] = Zs[16 * k * CFG::pitchZ];
+#pragma unroll
+  for (int k = 0; k < NZ; ++k)
+    if ((tid >> 4) + 16 * k < CFG::nb) zg[(size_t)16 * k * CFG::M] = q[k];
 }
 
 // ---- B: KG pairs of rows (+kh, -kh) of one plane: row FFTs, band update, inverse row FFTs, in place on zg ----------
@@ -213,9 +227,19 @@ __device__ __forceinline__ void mp_task_c(unsigned char* sm, const float* __rest
   if (MpTune<CFG>::pf_c) mp_prefetch_phase<CFG>(x4, strip, 0, tid);
   mp_wait_predecessor<CFG>();
   {
-    float4* Zs = reinterpret_cast<float4*>(sm + CFG::offZ);
-    const float4* zg = zgp + strip * 16;
-    for (int i = tid; i < CFG::nb * 16; i += 256) Zs[(i >> 4) * CFG::pitchZ + (i & 15)] = __ldcg(zg + (size_t)(i >> 4) * CFG::M + (i & 15));
+    // the strip's band rows: element i = tid + 256 k is row (tid >> 4) + 16 k, column tid & 15.  Every load is issued
+    // before the first one is stored (13 float4 in flight per thread at 1024^2) -- a rolled load/store loop pays the
+    // DRAM latency once per iteration and was 40 % of this pass's stall samples.
+    float4* Zs = reinterpret_cast<float4*>(sm + CFG::offZ) + (tid >> 4) * CFG::pitchZ + (tid & 15);
+    const float4* zg = zgp + strip * 16 + (size_t)(tid >> 4) * CFG::M + (tid & 15);
+    constexpr int NZ = (CFG::nb + 15) / 16;
+    float4 q[NZ];
+#pragma unroll
+    for (int k = 0; k < NZ; ++k)
+      if ((tid >> 4) + 16 * k < CFG::nb) q[k] = __ldcg(zg + (size_t)16 * k * CFG::M);
+#pragma unroll
+    for (int k = 0; k < NZ; ++k)
+      if ((tid >> 4) + 16 * k < CFG::nb) Zs[16 * k * CFG::pitchZ] = q[k];
   }
   {
     const long long p = pidx[gplane / C];
@@ -247,14 +271,11 @@ __global__ void __launch_bounds__(256, 2) ram_mp_pass_a(const float* __restrict_
   extern __shared__ __align__(16) unsigned char sm[];
   const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, plane = blockIdx.x / CFG::nstrips;
   mp_release_dependents<CFG>();
-  float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
-  for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
   // x of a whole-batch pass is far larger than L2 and is not met again before it has been evicted: stream it, and leave
   // L2 to the band rows that pass B is about to read
   unsigned long long pol_x;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_x));
-  __syncthreads();
-  mp_task_a<CFG>(sm, src, Zg + (size_t)plane * CFG::nb * CFG::M, plane, strip, pol_x);
+  mp_task_a<CFG>(sm, src, Zg + (size_t)plane * CFG::nb * CFG::M, plane, strip, pol_x, tab_ac);
 }
 template <class CFG, bool BANK>
 __global__ void __launch_bounds__(CFG::bThreads) ram_mp_pass_b(float4* __restrict__ Zg, const float* __restrict__ bank,
@@ -283,7 +304,7 @@ __global__ void __launch_bounds__(256, 2) ram_mp_pass_c(const float* __restrict_
   for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
   unsigned long long pol_stream;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  __syncthreads();
+  // no barrier here: the task reads the tables only behind its own first barrier, so their loads overlap its band-row loads
   mp_task_c<CFG, EPI>(sm, src, Zg + (size_t)plane * CFG::nb * CFG::M, pidx, n_bank, C, out, ep, plane, plane0 + plane, strip, pol_stream);
 }
 

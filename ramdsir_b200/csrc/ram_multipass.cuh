@@ -80,10 +80,14 @@ struct FftN<8, DIR> {
 // ===== pass A ==================================================================================
 // F1a of a polyphase sub-column on packed pairs (see s_f1_fft_tw_x2): rows (h1 + 16 j) HP + p
 template <class CFG, class LoadF4>
-RD_HD void m_f1_load_fft_tw_x2(LoadF4 ld, const unsigned char* sm, int strip, int p, int t, cf2 (&v)[16]) {
+RD_HD void m_f1_load_rows_x2(LoadF4 ld, int strip, int p, int t, cf2 (&v)[16]) {
   const int h1 = t >> 4, c4 = strip * 16 + (t & 15);
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = cf2_from(ld((size_t)((h1 + 16 * j) * CFG::HP + p) * CFG::M + c4));
+}
+template <class CFG, class LoadF4>
+RD_HD void m_f1_load_fft_tw_x2(LoadF4 ld, const unsigned char* sm, int strip, int p, int t, cf2 (&v)[16]) {
+  m_f1_load_rows_x2<CFG>(ld, strip, p, t, v);
   s_f1_fft_tw_x2<CFG>(sm, t, v);
 }
 
