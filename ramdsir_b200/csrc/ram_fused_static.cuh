@@ -168,12 +168,17 @@ struct SumA<CFG, K1, DIR, 0> {
   static RD_HD CX run(const CX (&y)[CFG::Q][4]) { return y[0][((K1 % 4) + 4) % 4]; }
 };
 
+// kh = k2 + 16 k1, k2 in [0, 15]: is the row inside the band whatever k2 is?  (Then the test folds away at compile
+// time: no compare / branch / reconvergence point around the emit or the gather of that residue.)
+template <class CFG>
+RD_HD constexpr bool band_always(int k1) { return 16 * k1 >= -CFG::b && 16 * k1 + 15 <= CFG::b; }
+
 template <class CFG, int K1>
 struct F1Out {   // emits band rows kh = k2 + 16 k1 for k1 = K1 .. MM-1
   template <class CX>
   static RD_HD void run(const CX (&y)[CFG::Q][4], float2* zcol, int k2) {
     const int kh = k2 + 16 * K1;
-    if (kh >= -CFG::b && kh <= CFG::b) {
+    if (band_always<CFG>(K1) || (kh >= -CFG::b && kh <= CFG::b)) {
       const CX o = SumA<CFG, K1, -1, CFG::Q - 1>::run(y);
       zcol[(size_t)(kh + CFG::b) * CFG::pitchZ * 2] = make_float2(cx_re(o), cx_im(o));
     }
@@ -249,7 +254,7 @@ RD_HD void s_inv_pruned(unsigned char* sm, int strip, int par, int u) {
   for (int i = 0; i < 2 * CFG::MM; ++i) {
     const int kh = k2 + 16 * (i - CFG::MM);
     CX v = cx_make<CX>(0.f, 0.f);
-    if (kh >= -CFG::b && kh <= CFG::b) {
+    if (band_always<CFG>(i - CFG::MM) || (kh >= -CFG::b && kh <= CFG::b)) {
       const float2 z = zcol[(size_t)(kh + CFG::b) * CFG::pitchZ * 2];
       v = cx_make<CX>(z.x, z.y);
     }

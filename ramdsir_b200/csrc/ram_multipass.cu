@@ -3,6 +3,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 #include "ram_internal.h"
 #include "ram_fused_host.h"
@@ -68,11 +69,13 @@ __device__ __forceinline__ void mp_task_a(unsigned char* sm, const float* __rest
   const int tid = threadIdx.x;
   const float4* x4 = reinterpret_cast<const float4*>(src + (size_t)plane * CFG::H * CFG::W);
   auto ld = [&](size_t off) { return mp_ldg_policy(x4 + off, pol_keep); };
-  for (int p = 0; p < CFG::HP; ++p) {
+  // one polyphase sub-column; FIRST (p = 0) also brings the tables in and stores Z where the others accumulate
+  auto sub_column = [&](auto first, int p) {
+    constexpr bool FIRST = decltype(first)::value;
     cf2 v[16];
     if (MpTune<CFG>::pf_a_next && p + 1 == CFG::HP) mp_prefetch_next_block<CFG>(src, tid);
     m_f1_load_rows_x2<CFG>(ld, strip, p, tid, v);
-    if (p == 0) {   // the tables travel behind the first sub-column's loads
+    if (FIRST) {   // the tables travel behind the first sub-column's loads
       float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
       for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
       __syncthreads();
@@ -83,10 +86,12 @@ __device__ __forceinline__ void mp_task_a(unsigned char* sm, const float* __rest
     for (int half = 0; half < 2; ++half) {
       s_f1_store_half_x2<CFG>(sm, tid, half, v);
       __syncthreads();
-      m_f1_pruned<CFG>(sm, p, half, tid);
+      m_f1_pruned<CFG, FIRST>(sm, p, half, tid);
       __syncthreads();
     }
-  }
+  };
+  sub_column(std::true_type{}, 0);
+  for (int p = 1; p < CFG::HP; ++p) sub_column(std::false_type{}, p);
   // element i = tid + 256 k of the strip's band rows is row (tid >> 4) + 16 k, column tid & 15
   const float4* Zs = reinterpret_cast<const float4*>(sm + CFG::offZ) + (tid >> 4) * CFG::pitchZ + (tid & 15);
   float4* zg = zgp + strip * 16 + (size_t)(tid >> 4) * CFG::M + (tid & 15);
@@ -269,7 +274,7 @@ __device__ __forceinline__ void mp_task_c(unsigned char* sm, const float* __rest
 template <class CFG>
 __global__ void __launch_bounds__(256, 2) ram_mp_pass_a(const float* __restrict__ src, float4* __restrict__ Zg, const float* __restrict__ tab_ac) {
   extern __shared__ __align__(16) unsigned char sm[];
-  const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, plane = blockIdx.x / CFG::nstrips;
+  const int strip = blockIdx.x % CFG::nstrips, plane = blockIdx.x / CFG::nstrips;
   mp_release_dependents<CFG>();
   // x of a whole-batch pass is far larger than L2 and is not met again before it has been evicted: stream it, and leave
   // L2 to the band rows that pass B is about to read

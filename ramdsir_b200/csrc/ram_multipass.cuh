@@ -91,57 +91,59 @@ RD_HD void m_f1_load_fft_tw_x2(LoadF4 ld, const unsigned char* sm, int strip, in
   s_f1_fft_tw_x2<CFG>(sm, t, v);
 }
 
-template <class CFG, int K1>
+// FIRST (sub-column p = 0) stores, the later sub-columns accumulate: a compile-time choice, so that the emit is
+// LDS (twiddle) [+ LDS (old)], 2 packed multiplies [+ 1 packed add], STS with no predicated copies around it.
+template <class CFG, int K1, bool FIRST>
 struct MF1Out {   // Zs[kh] (+)= TWP[p][kh] * sum_a W_16^(a k1) y[a][k1 mod 4]
-  static RD_HD void run(const cp (&y)[4][4], float2* zcol, const float2* twp, int k2, bool first) {
+  static RD_HD void run(const cp (&y)[4][4], float2* zcol, const float2* twp, int k2) {
     const int kh = k2 + 16 * K1;
-    if (kh >= -CFG::b && kh <= CFG::b) {
+    if (band_always<CFG>(K1) || (kh >= -CFG::b && kh <= CFG::b)) {
       cp o = SumA<CFG, K1, -1, 3>::run(y);
       const float2 w = twp[kh];
       o = cmul(o, cf{w.x, w.y});
       float2* z = zcol + (size_t)(kh + CFG::b) * CFG::pitchZ * 2;
-      if (!first) {
+      if (!FIRST) {
         const float2 old = *z;
         o = o + cp_make(old.x, old.y);
       }
       *z = make_float2(cp_re(o), cp_im(o));
     }
-    MF1Out<CFG, K1 + 1>::run(y, zcol, twp, k2, first);
+    MF1Out<CFG, K1 + 1, FIRST>::run(y, zcol, twp, k2);
   }
 };
-template <class CFG>
-struct MF1Out<CFG, CFG::MM> {
-  static RD_HD void run(const cp (&)[4][4], float2*, const float2*, int, bool) {}
+template <class CFG, bool FIRST>
+struct MF1Out<CFG, CFG::MM, FIRST> {
+  static RD_HD void run(const cp (&)[4][4], float2*, const float2*, int) {}
 };
 
 // Emit the band rows kh = k2 + 16 K1 from the finished 16-point transform X[k1 mod 16] (at v[pos16(.)]).
-template <class CFG, int K1>
+template <class CFG, int K1, bool FIRST>
 struct MF1OutFull {
-  static RD_HD void run(const cp (&v)[16], float2* zcol, const float2* twp, int k2, bool first) {
+  static RD_HD void run(const cp (&v)[16], float2* zcol, const float2* twp, int k2) {
     const int kh = k2 + 16 * K1;
-    if (kh >= -CFG::b && kh <= CFG::b) {
+    if (band_always<CFG>(K1) || (kh >= -CFG::b && kh <= CFG::b)) {
       cp o = v[pos16((K1 + 16) & 15)];
       const float2 w = twp[kh];
       o = cmul(o, cf{w.x, w.y});
       float2* z = zcol + (size_t)(kh + CFG::b) * CFG::pitchZ * 2;
-      if (!first) {
+      if (!FIRST) {
         const float2 old = *z;
         o = o + cp_make(old.x, old.y);
       }
       *z = make_float2(cp_re(o), cp_im(o));
     }
-    MF1OutFull<CFG, K1 + 1>::run(v, zcol, twp, k2, first);
+    MF1OutFull<CFG, K1 + 1, FIRST>::run(v, zcol, twp, k2);
   }
 };
-template <class CFG>
-struct MF1OutFull<CFG, CFG::MM> {
-  static RD_HD void run(const cp (&)[16], float2*, const float2*, int, bool) {}
+template <class CFG, bool FIRST>
+struct MF1OutFull<CFG, CFG::MM, FIRST> {
+  static RD_HD void run(const cp (&)[16], float2*, const float2*, int) {}
 };
 
 // Second stage of the 256-row sub-transform.  With a wide band (1024^2: 13 of the 16 residues k1 of every k2 are in
 // the band) the stage is a complete 16-point FFT over h1 -- 64 butterfly additions and 9 twiddles instead of 13
 // four-term twiddled sums; with a narrow band (512^2: 6.4 of 16) the pruned radix-4 + sums form is cheaper.
-template <class CFG>
+template <class CFG, bool FIRST>
 RD_HD void m_f1_pruned(unsigned char* sm, int p, int half, int u) {
   const int col = u & 1, c = (u >> 1) & 15, k2l = u >> 5, k2 = 8 * half + k2l;
   const float2* e = reinterpret_cast<const float2*>(sm + CFG::offE) + ((size_t)k2l * 16 * 16 + c) * 2 + col;
@@ -156,7 +158,7 @@ RD_HD void m_f1_pruned(unsigned char* sm, int p, int half, int u) {
       v[h1] = cp_make(t.x, t.y);
     }
     fft16<-1>(v);
-    MF1OutFull<CFG, -CFG::MM>::run(v, zcol, twp, k2, p == 0);
+    MF1OutFull<CFG, -CFG::MM, FIRST>::run(v, zcol, twp, k2);
   } else {
     cp y[4][4];
 #pragma unroll
@@ -168,7 +170,7 @@ RD_HD void m_f1_pruned(unsigned char* sm, int p, int half, int u) {
       }
       fft4<-1>(y[a][0], y[a][1], y[a][2], y[a][3]);
     }
-    MF1Out<CFG, -CFG::MM>::run(y, zcol, twp, k2, p == 0);
+    MF1Out<CFG, -CFG::MM, FIRST>::run(y, zcol, twp, k2);
   }
 }
 
@@ -184,7 +186,7 @@ RD_HD void m_inv_pruned(unsigned char* sm, int p, int par, int u) {
   for (int i = 0; i < 2 * CFG::MM; ++i) {
     const int kh = k2 + 16 * (i - CFG::MM);
     cp v = cp_make(0.f, 0.f);
-    if (kh >= -CFG::b && kh <= CFG::b) {
+    if (band_always<CFG>(i - CFG::MM) || (kh >= -CFG::b && kh <= CFG::b)) {
       const float2 z = zcol[(size_t)(kh + CFG::b) * CFG::pitchZ * 2];
       const float2 w = twp[kh];
       v = cmulc(cp_make(z.x, z.y), cf{w.x, w.y});   // x W_H^(-p kh)

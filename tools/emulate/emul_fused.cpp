@@ -190,7 +190,7 @@ static int run_all_mp(const float* src, const float* bank, const long long* pidx
           for (int half = 0; half < 2; ++half) {
             for (int t = 0; t < 256; ++t)
               s_f1_store_half_x2<CFG>(sm.data(), t, half, *reinterpret_cast<cf2(*)[16]>(&regs[(size_t)t * 32]));
-            for (int u = 0; u < 256; ++u) m_f1_pruned<CFG>(sm.data(), p, half, u);
+            for (int u = 0; u < 256; ++u) { if (p == 0) m_f1_pruned<CFG, true>(sm.data(), p, half, u); else m_f1_pruned<CFG, false>(sm.data(), p, half, u); }
           }
         }
         const float4* Zs = reinterpret_cast<const float4*>(sm.data() + CFG::offZ);
