@@ -32,7 +32,8 @@ __device__ __forceinline__ void mp_stg_policy(float4* p, float4 v, unsigned long
 //             its last wave vacates, load their tables (pass C: start on x) and only then wait for its results.
 //             512^2 -2.2 %, 1024^2 +3.7 % (slower)
 // Deeper prefetch (two sub-columns ahead +4 %, the whole strip at entry +11 %) and the next-block prefetch in pass C
-// (+2 %) were slower; the next block's band rows in pass B gave -0.3 % and were not kept.
+// (+2 %) were slower; the next block's band rows in pass B gave -0.3 % and were not kept; band-row stores with an
+// L2 evict_last policy (to keep the workspace resident between the passes) cost +5 %.
 template <class CFG>
 struct MpTune {
   static constexpr bool pf_c = true;
