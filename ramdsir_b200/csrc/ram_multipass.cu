@@ -17,6 +17,20 @@ __device__ __forceinline__ float4 mp_ldg_policy(const float4* p, unsigned long l
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
   return v;
 }
+// 16-byte global -> shared copies that need no registers (tables): issue early, wait in front of the barrier before first use
+__device__ __forceinline__ void mp_copy_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void mp_copy_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <bool ASYNC, int NT>
+__device__ __forceinline__ void mp_copy_table(void* smem_dst, const float* gsrc, int bytes, int tid) {
+  float4* t = reinterpret_cast<float4*>(smem_dst);
+  const float4* g = reinterpret_cast<const float4*>(gsrc);
+  for (int i = tid; i < bytes / 16; i += NT) {
+    if (ASYNC) mp_copy_async16(t + i, g + i);
+    else t[i] = g[i];
+  }
+}
 __device__ __forceinline__ void mp_stg_policy(float4* p, float4 v, unsigned long long pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
@@ -31,6 +45,8 @@ __device__ __forceinline__ void mp_stg_policy(float4* p, float4 v, unsigned long
 //  pdl        passes B and C are launched as programmatic dependents of the pass before them: their CTAs take the slots
 //             its last wave vacates, load their tables (pass C: start on x) and only then wait for its results.
 //             512^2 -2.2 %, 1024^2 +3.7 % (slower)
+//  async_tables  the per-CTA table copy as cp.async (no registers, no wait until the barrier before first use) instead
+//             of loads + stores: 1024^2 -0.8 %, 512^2 +1.8 % (slower, beside pdl)
 // Deeper prefetch (two sub-columns ahead +4 %, the whole strip at entry +11 %) and the next-block prefetch in pass C
 // (+2 %) were slower; the next block's band rows in pass B gave -0.3 % and were not kept; band-row stores with an
 // L2 evict_last policy (to keep the workspace resident between the passes) cost +5 %.
@@ -40,6 +56,7 @@ struct MpTune {
   static constexpr bool pf_a = CFG::H > 512;
   static constexpr bool pf_a_next = CFG::H > 512;
   static constexpr bool pdl = CFG::H <= 512;
+  static constexpr bool async_tables = CFG::H > 512;
 };
 constexpr int kMpSlots = 296;   // CTAs of pass A resident at once (2 per SM)
 template <class CFG> __device__ __forceinline__ void mp_release_dependents() { if (MpTune<CFG>::pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -77,8 +94,8 @@ __device__ __forceinline__ void mp_task_a(unsigned char* sm, const float* __rest
     if (MpTune<CFG>::pf_a_next && p + 1 == CFG::HP) mp_prefetch_next_block<CFG>(src, tid);
     m_f1_load_rows_x2<CFG>(ld, strip, p, tid, v);
     if (FIRST) {   // the tables travel behind the first sub-column's loads
-      float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
-      for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
+      mp_copy_table<MpTune<CFG>::async_tables, 256>(sm + CFG::offTab, tab_ac, CFG::tabBytes, tid);
+      mp_copy_async_wait();
       __syncthreads();
     }
     s_f1_fft_tw_x2<CFG>(sm, tid, v);
@@ -163,6 +180,7 @@ __device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, f
           if (tid + NT * k < CFG::nb) P[r * CFG::nb + tid + NT * k] = prow[tid + NT * k];
       }
   }
+  mp_copy_async_wait();      // the caller's table copy
   __syncthreads();
   for (int t = tid; t < ng * 2 * CFG::N1w; t += NT) {
     const int g = t / (2 * CFG::N1w), tt = t % (2 * CFG::N1w);
@@ -175,28 +193,36 @@ __device__ __forceinline__ void mp_task_b(unsigned char* sm, const float* tab, f
   }
   __syncthreads();
   const size_t patch_px = (size_t)CFG::nb * CFG::nb;
-  const int nband = 2 * (CFG::b + 1);
+  // band bins row by row (two rows at a time when a row's b + 1 bins fill at most half of the CTA): no divisions
+  constexpr int P2 = (CFG::b + 1 <= NT / 2) ? NT / 2 : NT, RPI = NT / P2;
+  static_assert(CFG::b + 1 <= P2, "one pass of the CTA covers a row of band bins");
+  const int kwb = tid % P2, sub = tid / P2;
   if (BANK) {
     float* patch = bank_out + (size_t)plane * patch_px;
-    for (int t = tid; t < ng * nband; t += NT) {
-      const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
-      if (live(2 * g + srow)) m_band<CFG, true>(R + (size_t)g * RP, D + g * DP, tab, nullptr, patch, 0.f, 0.f, kh0 + g, srow, tt % (CFG::b + 1));
+#pragma unroll
+    for (int r0 = 0; r0 < 2 * KG; r0 += RPI) {
+      const int r = r0 + sub, g = r >> 1;
+      if (r < 2 * ng && kwb <= CFG::b && live(r)) m_band<CFG, true>(R + (size_t)g * RP, D + g * DP, tab, nullptr, patch, 0.f, 0.f, kh0 + g, r & 1, kwb);
     }
   } else {
     {
       const float* P = reinterpret_cast<const float*>(sm + CFG::bOffP);
-      for (int t = tid; t < ng * nband; t += NT) {
-        const int g = t / nband, tt = t % nband, srow = tt / (CFG::b + 1);
-        if (live(2 * g + srow)) m_band<CFG, false>(R + (size_t)g * RP, D + g * DP, tab, P + g * 2 * CFG::nb, nullptr, omr, dc_add, kh0 + g, srow, tt % (CFG::b + 1));
+#pragma unroll
+      for (int r0 = 0; r0 < 2 * KG; r0 += RPI) {
+        const int r = r0 + sub, g = r >> 1;
+        if (r < 2 * ng && kwb <= CFG::b && live(r)) m_band<CFG, false>(R + (size_t)g * RP, D + g * DP, tab, P + g * 2 * CFG::nb, nullptr, omr, dc_add, kh0 + g, r & 1, kwb);
       }
     }
     __syncthreads();
     for (int i = tid; i < ng * RP; i += NT) R[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // everything off the band is zero
     __syncthreads();
-    for (int t = tid; t < ng * 2 * CFG::nb; t += NT) {
-      const int g = t / (2 * CFG::nb), tt = t % (2 * CFG::nb), srow = tt / CFG::nb;
-      if (live(2 * g + srow)) m_put_v<CFG>(R + (size_t)g * RP, D + g * DP, tab, kh0 + g, srow, tt % CFG::nb);
-    }
+#pragma unroll
+    for (int r = 0; r < 2 * KG; ++r)       // row by row: no division, the row's offsets are compile-time constants
+      if (r < 2 * ng && live(r)) {
+#pragma unroll
+        for (int k = 0; k < (CFG::nb + NT - 1) / NT; ++k)
+          if (tid + NT * k < CFG::nb) m_put_v<CFG>(R + (size_t)(r >> 1) * RP, D + (r >> 1) * DP, tab, kh0 + (r >> 1), r & 1, tid + NT * k);
+      }
     __syncthreads();
     for (int t = tid; t < ng * 32; t += NT) {
       const int g = t / 32, tt = t % 32;
@@ -251,6 +277,7 @@ __device__ __forceinline__ void mp_task_c(unsigned char* sm, const float* __rest
     const long long p = pidx[gplane / C];
     if (p < 0 || p >= (long long)n_bank) ep = mp_poisoned(ep);
   }
+  mp_copy_async_wait();      // the caller's table copy
   __syncthreads();
   float4* y4 = reinterpret_cast<float4*>(out + plane * plane_px);
   auto ld = [&](size_t off) { return mp_ldg_policy(x4 + off, pol_stream); };
@@ -292,8 +319,7 @@ __global__ void __launch_bounds__(CFG::bThreads) ram_mp_pass_b(float4* __restric
   // they are still in L2 -- and finishes with the first planes, which is where pass C (forward order) starts reading.
   const int tid = threadIdx.x, kg = blockIdx.x % CFG::nkg, plane = (int)(gridDim.x / CFG::nkg) - 1 - (int)(blockIdx.x / CFG::nkg);
   mp_release_dependents<CFG>();
-  float4* t = reinterpret_cast<float4*>(sm + CFG::bOffTab);
-  for (int i = tid; i < CFG::bTabBytes / 16; i += CFG::bThreads) t[i] = reinterpret_cast<const float4*>(tab_b)[i];
+  mp_copy_table<MpTune<CFG>::async_tables, CFG::bThreads>(sm + CFG::bOffTab, tab_b, CFG::bTabBytes, tid);
   mp_wait_predecessor<CFG>();
   // no barrier here: the task reads the tables only behind its own first barrier, so their loads overlap its row loads
   // `plane` indexes this chunk's workspace and (bank mode) output; plane0 + plane is the batch-global plane whose
@@ -306,8 +332,7 @@ __global__ void __launch_bounds__(256, 2) ram_mp_pass_c(const float* __restrict_
     const int64_t* __restrict__ pidx, int n_bank, int C, float* __restrict__ out, EPI ep, const float* __restrict__ tab_ac, int plane0) {
   extern __shared__ __align__(16) unsigned char sm[];
   const int tid = threadIdx.x, strip = blockIdx.x % CFG::nstrips, plane = blockIdx.x / CFG::nstrips;
-  float4* t = reinterpret_cast<float4*>(sm + CFG::offTab);
-  for (int i = tid; i < CFG::tabBytes / 16; i += 256) t[i] = reinterpret_cast<const float4*>(tab_ac)[i];
+  mp_copy_table<MpTune<CFG>::async_tables, 256>(sm + CFG::offTab, tab_ac, CFG::tabBytes, tid);
   unsigned long long pol_stream;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
   // no barrier here: the task reads the tables only behind its own first barrier, so their loads overlap its band-row loads
