@@ -250,3 +250,63 @@ def ram_mix_batch(src: torch.Tensor, bank: torch.Tensor, partner_idx, ratio_k, L
             if t is not None:
                 t.record_stream(cur)
     return out
+
+
+class MixCall:
+    """A validated, argument-bound `ram_mix_batch`: everything that call does before its launch -- shape / dtype /
+    overlap checks, index upload, workspace -- happens once, here; `call()` afterwards is one C-ABI call
+    (ramdsir_mix_dual_f32 / _u8) with the bound pointers.  For loops that re-launch on the same buffers (a ring of
+    prefetched batches): the host side of a launch drops from tens of microseconds of Python to a few, which is what
+    keeps the automatic tail overlap of consecutive 256-image launches (88 us each) fed when the host is busy.
+
+    The stream is fixed at construction (`stream`, default: torch's current stream then).  The object keeps every tensor
+    it was given alive; the caller keeps the OBJECT alive until the launches it enqueued have completed, and must not
+    free or reshape the tensors underneath it.  Results are those of ram_mix_batch with the same arguments, bit for bit.
+    """
+
+    def __init__(self, src, bank, partner_idx, ratio_k, out, L=0.1, ratio_den=10, clip=(-math.inf, math.inf), scale=1.0, shift=0.0,
+                 stream=None, workspace=None, independent=False, serial=False, clean_out=None):
+        src = _need_cuda_src(src, "src")
+        bank = _need_cuda_f32(bank, "bank", 4)
+        bsz, c, h, w = src.shape
+        b = band_halfwidth(h, w, L)
+        nb = 2 * b + 1
+        if tuple(bank.shape[1:]) != (c, nb, nb) or bank.device != src.device:
+            raise ValueError("bank must be [N, %d, %d, %d] on %s, got %s on %s"
+                             % (c, nb, nb, src.device, tuple(bank.shape), bank.device))
+        _need_cuda_f32(out, "out", 4)
+        if out.shape != src.shape or _overlap(out, src):
+            raise ValueError("out must match src's shape and must not overlap it")
+        if clean_out is not None:
+            _need_cuda_f32(clean_out, "clean_out", 4)
+            if clean_out.shape != src.shape or _overlap(clean_out, src) or _overlap(clean_out, out):
+                raise ValueError("clean_out must match src's shape and overlap neither src nor out")
+        if src.dtype == torch.uint8 and not u8_supported(c, h, w, b):
+            raise ValueError("uint8 sources of shape %s are not read directly; pass src.float()" % (tuple(src.shape),))
+        flags = (_lib.FLAG_INDEPENDENT if independent else 0) | (_lib.FLAG_SERIAL if serial else 0)
+        lib = _lib.load()
+        lo, hi = float(clip[0]), float(clip[1])
+        with _on_stream(src.device, stream) as cur:
+            pidx = _index_tensor(partner_idx, torch.int64, src.device, "partner_idx", bsz, 0, bank.shape[0] - 1)
+            rk = _index_tensor(ratio_k, torch.int32, src.device, "ratio_k", bsz, 0, int(ratio_den))
+            clean_ptr = None if clean_out is None else clean_out.data_ptr()
+            head = (src.data_ptr(), bank.data_ptr(), pidx.data_ptr(), rk.data_ptr(), out.data_ptr(), clean_ptr,
+                    bsz, c, h, w, b, bank.shape[0], int(ratio_den), lo, hi, float(scale), float(shift))
+            if src.dtype == torch.uint8:
+                ws = None
+                self._fn, self._args = lib.ramdsir_mix_dual_u8, head + (int(cur.cuda_stream), flags)
+            else:
+                ws, ws_ptr, ws_n = _workspace(int(lib.ramdsir_workspace_bytes_ex(bsz, c, h, w, b, flags)), src.device, workspace)
+                self._fn, self._args = lib.ramdsir_mix_dual_f32, head + (ws_ptr, ws_n, int(cur.cuda_stream), flags)
+            self.stream = cur
+        self.out = out
+        self._keep = (src, bank, pidx, rk, out, clean_out, ws)
+
+    def call(self):
+        """Enqueue the launch on the stream chosen at construction; returns `out`."""
+        rc = self._fn(*self._args)
+        if rc:
+            _lib.check(rc)
+        return self.out
+
+    __call__ = call

@@ -117,3 +117,12 @@ def test_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "ram_oracle" not in text, f
+
+
+def test_bound_launch_refuses_host_tensors():
+    """MixCall is the GPU path only: host tensors are refused at binding (no CPU fallback anywhere in the package)."""
+    import torch
+    import ramdsir_b200 as R
+    x = torch.zeros(1, 1, 64, 64)
+    with pytest.raises(TypeError):
+        R.MixCall(x, torch.zeros(1, 1, 13, 13), [0], [1], torch.empty_like(x))

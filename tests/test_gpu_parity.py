@@ -542,6 +542,39 @@ def test_side_stream_orders_uploads_conversions_and_kernel(R):
         assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("shape,u8", [((24, 3, 256, 256), False), ((24, 3, 256, 256), True), ((6, 1, 384, 384), False),
+                                      ((2, 3, 512, 512), False)])
+def test_bound_launch_matches_ram_mix_batch(R, shape, u8):
+    """MixCall (checks, uploads and workspace done once; call() = one C-ABI launch) gives the bits of ram_mix_batch,
+    launch after launch over a rotation of buffers, with and without the automatic overlap."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B, C, H, W = shape
+    srcs = [torch.randint(0, 256, shape, device="cuda", generator=g).float() for _ in range(2)]
+    if u8:
+        srcs = [s.to(torch.uint8) for s in srcs]
+    bank = R.build_amp_bank(torch.randint(0, 256, (5, C, H, W), device="cuda", generator=g).float())
+    rs = np.random.RandomState(4)
+    pidx, rk = rs.randint(0, 5, B), rs.randint(1, 11, B).astype(np.int32)       # host values: uploaded once, at binding
+    e = R.FUNDUS_EPILOGUE
+    want = [R.ram_mix_batch(s, bank, pidx, rk, clip=e[:2], scale=e[2], shift=e[3], serial=True) for s in srcs]
+    outs = [torch.empty_like(want[0]) for _ in range(3)]
+    for serial in (False, True):
+        calls = {(i, j): R.MixCall(srcs[i], bank, pidx, rk, outs[j], clip=e[:2], scale=e[2], shift=e[3], serial=serial)
+                 for i in range(2) for j in range(3)}
+        for o in outs:
+            o.fill_(float("nan"))
+        for k in range(12):
+            got = calls[(k % 2, k % 3)]()
+            assert got is outs[k % 3]
+        torch.cuda.synchronize()
+        for k in range(9, 12):                                                  # the last write of every output buffer
+            assert torch.equal(outs[k % 3], want[k % 2])
+    with pytest.raises(ValueError):
+        R.MixCall(srcs[0], bank, pidx, rk, torch.empty(1, C, H, W, device="cuda"))   # out does not match src
+    with pytest.raises(ValueError):
+        R.MixCall(srcs[0], bank, pidx[:-1], rk, outs[0])
+
+
 def test_auto_overlap_keeps_stream_order_between_dependent_launches(R):
     """Back-to-back launches overlap their tails only when their buffers are disjoint.  A chain in which every launch
     reads what the previous one wrote (and a launch that overwrites the previous one's source) must give exactly the
